@@ -1,0 +1,370 @@
+"""Oracle-backed stand-in for the ``sparseconvnet`` module surface.
+
+TEST INFRASTRUCTURE ONLY (see oracle/scn_oracle.py header; PARITY UNPINNED).
+It lets the reference's own model files (``/root/reference/src/networks/*.py``) be
+imported verbatim on CPU (``sys.modules['sparseconvnet'] = this``) to generate golden
+vectors, and it is the CPU baseline timed by ``bench.py --impl reference``.
+The product package never imports it.
+
+Surface restated: every ``scn.*`` symbol the reference touches.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import scn_oracle as O
+
+__all__ = [
+    "SparseConvNetTensor", "Metadata", "InputLayer", "OutputLayer", "SubmanifoldConvolution",
+    "Convolution", "Deconvolution", "BatchNormalization", "BatchNormReLU", "BatchNormLeakyReLU",
+    "LeakyReLU", "ReLU", "Tanh", "Sigmoid", "Identity", "AddTable", "SparseToDense", "Sequential",
+]
+
+
+class Metadata:
+    """Per-forward cache: active sites per spatial size + rulebooks."""
+
+    def __init__(self, dimension=3):
+        self.dimension = dimension
+        self.levels = {}          # spatial tuple -> int64 [N,4] coords in row order
+        self.subm = {}            # (spatial, filter) -> rules
+        self.strided = {}         # (in_spatial, filter, stride) -> (out_spatial, rules)
+        self.row_of_input = None
+        self.batch_size = 0
+        self.input_spatial = None
+
+    def get_subm(self, spatial, filt):
+        key = (spatial, filt)
+        if key not in self.subm:
+            self.subm[key] = O.submanifold_rulebook(self.levels[spatial], filt)
+        return self.subm[key]
+
+    def get_strided(self, spatial, filt, stride):
+        key = (spatial, filt, stride)
+        if key not in self.strided:
+            out_coords, rules, out_spatial = O.strided_rulebook(self.levels[spatial], filt, stride, spatial)
+            if out_spatial not in self.levels:
+                self.levels[out_spatial] = out_coords
+            else:
+                # fine->coarse requested again on an existing coarse grid: re-index to it
+                have = self.levels[out_spatial]
+                remap = O._lookup(*_sorted(have), O.pack_keys(out_coords))
+                rules = [np.stack([r[:, 0], remap[r[:, 1]]], 1) if len(r) else r for r in rules]
+            self.strided[key] = (out_spatial, rules)
+        return self.strided[key]
+
+
+def _sorted(coords):
+    k = O.pack_keys(coords)
+    o = np.argsort(k, kind="stable")
+    return k[o], o
+
+
+class SparseConvNetTensor:
+    def __init__(self, features=None, metadata=None, spatial_size=None):
+        self.features = features
+        self.metadata = metadata
+        self.spatial_size = spatial_size
+
+    def get_spatial_locations(self, spatial_size=None):
+        sp = tuple(int(v) for v in (self.spatial_size if spatial_size is None else spatial_size))
+        return torch.as_tensor(self.metadata.levels[sp], dtype=torch.long)
+
+    def batch_size(self):
+        return self.metadata.batch_size
+
+    def cpu(self):
+        return self
+
+    def __repr__(self):
+        return f"SparseConvNetTensor<oracle>(features={tuple(self.features.shape)}, spatial={self.spatial_size})"
+
+
+def _sp(t):
+    return tuple(int(v) for v in t.spatial_size)
+
+
+# ---------------------------------------------------------------- autograd glue
+
+
+class _InputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, rows, n_active, mode):
+        ctx.rows, ctx.mode = rows, mode
+        return O.input_layer_forward(feats, rows, n_active, mode)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return O.input_layer_backward(dout.contiguous(), ctx.rows, ctx.mode), None, None, None
+
+
+class _OutputFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, rows):
+        ctx.rows, ctx.n = rows, feats.shape[0]
+        return O.output_layer_forward(feats, rows)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return O.output_layer_backward(dout.contiguous(), ctx.rows, ctx.n), None
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, rules, n_out):
+        ctx.rules = rules
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight)
+        return O.conv_forward(x, weight.view(weight.shape[0], weight.shape[-2], weight.shape[-1]), bias, rules, n_out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, weight = ctx.saved_tensors
+        w3 = weight.view(weight.shape[0], weight.shape[-2], weight.shape[-1])
+        dx, dw, db = O.conv_backward(x, w3, ctx.has_bias, ctx.rules, dout.contiguous())
+        return dx, dw.view_as(weight), db, None, None
+
+
+class _BNFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, rm, rv, training, eps, momentum, leak):
+        out, mean, invstd = O.batchnorm_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak)
+        ctx.training, ctx.leak = training, leak
+        ctx.save_for_backward(x, out, gamma, mean, invstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, out, gamma, mean, invstd = ctx.saved_tensors
+        dx, dg, db = O.batchnorm_backward(x, out, gamma, mean, invstd, dout.contiguous(), ctx.training, ctx.leak)
+        return dx, dg, db, None, None, None, None, None, None
+
+
+class _LeakyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, leak):
+        ctx.leak = leak
+        ctx.save_for_backward(x)
+        return O.leaky_relu_forward(x, leak)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        return O.leaky_relu_backward(x, dout, ctx.leak), None
+
+
+class _S2DFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, coords, spatial, batch_size):
+        ctx.coords = coords
+        return O.sparse_to_dense_forward(x, coords, spatial, batch_size)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return O.sparse_to_dense_backward(dout, ctx.coords), None, None, None
+
+
+# ---------------------------------------------------------------- modules
+
+
+class InputLayer(nn.Module):
+    """scn.InputLayer(dimension, spatial_size, mode=3)  (src/networks/resnet.py:26-29,40-43)."""
+
+    def __init__(self, dimension, spatial_size, mode=3):
+        super().__init__()
+        self.dimension = dimension
+        self.spatial_size = torch.LongTensor(list(O.as_triple(spatial_size, dimension)))
+        self.mode = mode
+
+    def forward(self, input):
+        coords, feats = input[0], input[1]
+        batch_size = int(input[2]) if len(input) > 2 else 0
+        coords = torch.as_tensor(coords).cpu().long().numpy()
+        if coords.shape[1] == self.dimension:       # single sample: add batch column 0
+            coords = np.concatenate([coords, np.zeros((coords.shape[0], 1), np.int64)], 1)
+        feats = torch.as_tensor(feats)
+        md = Metadata(self.dimension)
+        rows, active = O.input_layer_rules(coords, self.mode)
+        sp = tuple(int(v) for v in self.spatial_size)
+        md.levels[sp] = active
+        md.row_of_input = rows
+        md.input_spatial = sp
+        md.batch_size = max(batch_size, int(coords[:, -1].max()) + 1 if coords.shape[0] else 0)
+        out = SparseConvNetTensor(metadata=md, spatial_size=self.spatial_size)
+        out.features = _InputFn.apply(feats, rows, active.shape[0], self.mode)
+        return out
+
+
+class OutputLayer(nn.Module):
+    def __init__(self, dimension):
+        super().__init__()
+        self.dimension = dimension
+
+    def forward(self, input):
+        return _OutputFn.apply(input.features, input.metadata.row_of_input)
+
+
+def _init_weight(k, n_in, n_out):
+    w = torch.empty(k, 1, n_in, n_out)
+    w.normal_(0, math.sqrt(2.0 / (n_in * k)))
+    return nn.Parameter(w)
+
+
+class SubmanifoldConvolution(nn.Module):
+    """(dimension, nIn, nOut, filter_size, bias, groups=1)  (sparse_building_blocks.py:29-34)."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
+        super().__init__()
+        assert groups == 1
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = O.as_triple(filter_size, dimension)
+        self.filter_volume = int(np.prod(self.filter_size))
+        self.weight = _init_weight(self.filter_volume, nIn, nOut)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn
+        md, sp = input.metadata, _sp(input)
+        rules = md.get_subm(sp, self.filter_size)
+        out = SparseConvNetTensor(metadata=md, spatial_size=input.spatial_size)
+        out.features = _ConvFn.apply(input.features, self.weight, self.bias, rules, input.features.shape[0])
+        return out
+
+
+class Convolution(nn.Module):
+    """(dimension, nIn, nOut, filter_size, filter_stride, bias)  (sparse_building_blocks.py:110-117)."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        assert groups == 1
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = O.as_triple(filter_size, dimension)
+        self.filter_stride = O.as_triple(filter_stride, dimension)
+        self.filter_volume = int(np.prod(self.filter_size))
+        self.weight = _init_weight(self.filter_volume, nIn, nOut)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn
+        md, sp = input.metadata, _sp(input)
+        out_sp, rules = md.get_strided(sp, self.filter_size, self.filter_stride)
+        out = SparseConvNetTensor(metadata=md, spatial_size=torch.LongTensor(list(out_sp)))
+        out.features = _ConvFn.apply(input.features, self.weight, self.bias, rules, md.levels[out_sp].shape[0])
+        return out
+
+
+class Deconvolution(nn.Module):
+    """(dimension, nIn, nOut, filter_size, filter_stride, bias)  (sparse_building_blocks.py:207-213)."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = O.as_triple(filter_size, dimension)
+        self.filter_stride = O.as_triple(filter_stride, dimension)
+        self.filter_volume = int(np.prod(self.filter_size))
+        self.weight = _init_weight(self.filter_volume, nIn, nOut)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def forward(self, input):
+        md, sp = input.metadata, _sp(input)
+        fine = tuple((sp[a] - 1) * self.filter_stride[a] + self.filter_size[a] for a in range(3))
+        assert fine in md.levels, "Deconvolution needs the fine grid to exist in the metadata (App. A.7)"
+        _, rules = md.get_strided(fine, self.filter_size, self.filter_stride)
+        out = SparseConvNetTensor(metadata=md, spatial_size=torch.LongTensor(list(fine)))
+        out.features = _ConvFn.apply(input.features, self.weight, self.bias, O.swap_rules(rules),
+                                     md.levels[fine].shape[0])
+        return out
+
+
+class BatchNormalization(nn.Module):
+    """(nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1)  (sparse_building_blocks.py:39,122)."""
+
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1):
+        super().__init__()
+        self.nPlanes, self.eps, self.momentum, self.affine, self.leakiness = nPlanes, eps, momentum, affine, leakiness
+        self.register_buffer("running_mean", torch.zeros(nPlanes))
+        self.register_buffer("running_var", torch.ones(nPlanes))
+        if affine:
+            self.weight = nn.Parameter(torch.ones(nPlanes))
+            self.bias = nn.Parameter(torch.zeros(nPlanes))
+        else:
+            self.weight = self.bias = None
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
+        out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
+        out.features = _BNFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
+                                   self.training, self.eps, self.momentum, float(self.leakiness))
+        return out
+
+
+class BatchNormReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9):
+        super().__init__(nPlanes, eps, momentum, True, 0)
+
+
+class BatchNormLeakyReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, leakiness=0.333):
+        super().__init__(nPlanes, eps, momentum, True, leakiness)
+
+
+class LeakyReLU(nn.Module):
+    def __init__(self, leak=1.0 / 3.0):
+        super().__init__()
+        self.leak = leak
+
+    def forward(self, input):
+        out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
+        out.features = _LeakyFn.apply(input.features, self.leak)
+        return out
+
+
+class ReLU(LeakyReLU):
+    def __init__(self):
+        super().__init__(0.0)
+
+
+class Tanh(nn.Module):
+    def forward(self, input):
+        out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
+        out.features = torch.tanh(input.features)
+        return out
+
+
+class Sigmoid(nn.Module):
+    def forward(self, input):
+        out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
+        out.features = torch.sigmoid(input.features)
+        return out
+
+
+class Identity(nn.Module):
+    def forward(self, input):
+        return input
+
+
+class AddTable(nn.Module):
+    def forward(self, input):
+        out = SparseConvNetTensor(metadata=input[0].metadata, spatial_size=input[0].spatial_size)
+        out.features = sum(t.features for t in input)
+        return out
+
+
+class SparseToDense(nn.Module):
+    """(dimension, nPlanes)  (src/networks/resnet.py:123-125)."""
+
+    def __init__(self, dimension, nPlanes):
+        super().__init__()
+        self.dimension, self.nPlanes = dimension, nPlanes
+
+    def forward(self, input):
+        md, sp = input.metadata, _sp(input)
+        return _S2DFn.apply(input.features, md.levels[sp], sp, md.batch_size)
+
+
+class Sequential(nn.Sequential):
+    pass
