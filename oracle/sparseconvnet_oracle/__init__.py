@@ -25,6 +25,54 @@ __all__ = [
 ]
 
 
+# Stated-numerics emulation (tests only).  The CUDA path has three modes (sparseeventid_b200/scn/config.py):
+#   fp32 : nothing rounded                              -> NUMERICS all False
+#   mixed: bf16 tensor-core operands, fp32 storage      -> operand_round
+#   bf16 : bf16 operands AND bf16 feature storage       -> operand_round + storage_round
+# With these flags the oracle does float64 arithmetic on exactly the values the kernels see, so the
+# comparison isolates the kernels' own arithmetic from the precision the mode states.
+NUMERICS = {"operand_round": False, "storage_round": False}
+
+
+def set_numerics(mode: str):
+    NUMERICS["operand_round"] = mode in ("mixed", "bf16")
+    NUMERICS["storage_round"] = mode == "bf16"
+
+
+def _bf16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+def _rs(t):
+    return _bf16(t) if NUMERICS["storage_round"] else t
+
+
+def _tensor_core_shape(k, n_in, n_out):
+    """Mirror of scn_conv_uses_tensor_cores(): only these shapes round their operands to bf16."""
+    return n_in % 32 == 0 and n_out % 32 == 0 and n_in <= 256 and n_out <= 256 and k <= 128
+
+
+def _ro(t, k, n_in, n_out):
+    if NUMERICS["operand_round"] and _tensor_core_shape(k, n_in, n_out):
+        return _bf16(t)
+    return t
+
+
+class _RoundStorage(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return _bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def round_storage(t):
+    """Differentiable bf16 rounding (identity backward): a torch ``.to(bfloat16)`` cast in the GPU pipeline."""
+    return _RoundStorage.apply(t)
+
+
 class Metadata:
     """Per-forward cache: active sites per spatial size + rulebooks."""
 
@@ -119,14 +167,20 @@ class _ConvFn(torch.autograd.Function):
         ctx.rules = rules
         ctx.has_bias = bias is not None
         ctx.save_for_backward(x, weight)
-        return O.conv_forward(x, weight.view(weight.shape[0], weight.shape[-2], weight.shape[-1]), bias, rules, n_out)
+        w3 = weight.view(weight.shape[0], weight.shape[-2], weight.shape[-1])
+        k, cin, cout = w3.shape
+        return _rs(O.conv_forward(_ro(x, k, cin, cout), _ro(w3, k, cin, cout), bias, rules, n_out))
 
     @staticmethod
     def backward(ctx, dout):
         x, weight = ctx.saved_tensors
         w3 = weight.view(weight.shape[0], weight.shape[-2], weight.shape[-1])
-        dx, dw, db = O.conv_backward(x, w3, ctx.has_bias, ctx.rules, dout.contiguous())
-        return dx, dw.view_as(weight), db, None, None
+        k, cin, cout = w3.shape
+        dx, dw, db = O.conv_backward(_ro(x, k, cin, cout), _ro(w3, k, cin, cout), ctx.has_bias, ctx.rules,
+                                     _ro(dout.contiguous(), k, cin, cout))
+        if ctx.has_bias:
+            db = dout.sum(0)
+        return _rs(dx), dw.view_as(weight), db, None, None
 
 
 class _BNFn(torch.autograd.Function):
@@ -135,13 +189,13 @@ class _BNFn(torch.autograd.Function):
         out, mean, invstd = O.batchnorm_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak)
         ctx.training, ctx.leak = training, leak
         ctx.save_for_backward(x, out, gamma, mean, invstd)
-        return out
+        return _rs(out)
 
     @staticmethod
     def backward(ctx, dout):
         x, out, gamma, mean, invstd = ctx.saved_tensors
         dx, dg, db = O.batchnorm_backward(x, out, gamma, mean, invstd, dout.contiguous(), ctx.training, ctx.leak)
-        return dx, dg, db, None, None, None, None, None, None
+        return _rs(dx), dg, db, None, None, None, None, None, None
 
 
 class _LeakyFn(torch.autograd.Function):
@@ -149,12 +203,22 @@ class _LeakyFn(torch.autograd.Function):
     def forward(ctx, x, leak):
         ctx.leak = leak
         ctx.save_for_backward(x)
-        return O.leaky_relu_forward(x, leak)
+        return _rs(O.leaky_relu_forward(x, leak))
 
     @staticmethod
     def backward(ctx, dout):
         (x,) = ctx.saved_tensors
-        return O.leaky_relu_backward(x, dout, ctx.leak), None
+        return _rs(O.leaky_relu_backward(x, dout, ctx.leak)), None
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return _rs(a + b)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, dout
 
 
 class _S2DFn(torch.autograd.Function):
@@ -165,7 +229,7 @@ class _S2DFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        return O.sparse_to_dense_backward(dout, ctx.coords), None, None, None
+        return _rs(O.sparse_to_dense_backward(dout, ctx.coords)), None, None, None
 
 
 # ---------------------------------------------------------------- modules
@@ -350,7 +414,10 @@ class Identity(nn.Module):
 class AddTable(nn.Module):
     def forward(self, input):
         out = SparseConvNetTensor(metadata=input[0].metadata, spatial_size=input[0].spatial_size)
-        out.features = sum(t.features for t in input)
+        feats = input[0].features
+        for t in input[1:]:
+            feats = _AddFn.apply(feats, t.features)
+        out.features = feats
         return out
 
 

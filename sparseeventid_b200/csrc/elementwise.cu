@@ -1,0 +1,543 @@
+// Bandwidth-bound layers: BatchNormalization(+leaky), LeakyReLU, AddTable, InputLayer/OutputLayer
+// feature movement, SparseToDense.  Replace SCN's BatchNormalization.cu / LeakyReLU.cu /
+// IOLayers.cu / SparseToDense.cu (reference call sites
+// src/networks/sparse_building_blocks.py:39,45,80-82,96-98,122,128; src/networks/resnet.py:123-125,143).
+// All kernels are HBM-bound: 16-byte (fp32) / 8-byte (bf16) vector accesses along channels,
+// fp32 math, column reductions finished with fp64 atomics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedRows = 256;   // rows per block in column reductions
+
+// ---------------------------------------------------------------------------------------------
+// Column reductions over [n, C]: each thread owns VEC adjacent channels and strides over rows.
+// F::eval(row, c0, out_a[VEC], out_b[VEC]) yields the two per-element quantities to be summed.
+// ---------------------------------------------------------------------------------------------
+template <int VEC, typename F>
+__global__ void __launch_bounds__(kRedThreads) k_col_reduce2(F f, int64_t n, int C, double* __restrict__ acc /*[2][C]*/) {
+  extern __shared__ float sred[];   // [RY][CV][2*VEC]
+  const int CV = C / VEC;
+  const int RY = kRedThreads / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  float a[VEC], b[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) a[v] = b[v] = 0.f;
+  const int64_t r0 = (int64_t)blockIdx.x * kRedRows;
+  const int64_t r1 = r0 + kRedRows < n ? r0 + kRedRows : n;
+  if (ty < RY) {
+    for (int64_t r = r0 + ty; r < r1; r += RY) {
+      float va[VEC], vb[VEC];
+      f.eval(r, tx * VEC, va, vb);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        a[v] += va[v];
+        b[v] += vb[v];
+      }
+    }
+    float* dst = sred + ((size_t)ty * CV + tx) * 2 * VEC;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      dst[v] = a[v];
+      dst[VEC + v] = b[v];
+    }
+  }
+  __syncthreads();
+  // first CV*VEC*2 threads (looped) sum over ty and publish
+  for (int i = threadIdx.x; i < CV * 2 * VEC; i += kRedThreads) {
+    int cx = i / (2 * VEC), w = i % (2 * VEC);
+    float s = 0.f;
+    for (int y = 0; y < RY; ++y) s += sred[((size_t)y * CV + cx) * 2 * VEC + w];
+    int which = w / VEC, c = cx * VEC + (w % VEC);
+    if (F::kTwo || which == 0) atomicAdd(acc + (size_t)which * C + c, (double)s);
+  }
+}
+
+template <typename T, int VEC> struct LoadVec;
+template <typename T> struct LoadVec<T, 4> {
+  static __device__ __forceinline__ void ld(const T* p, float* o) {
+    float4 v = ld4(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  }
+  static __device__ __forceinline__ void st(T* p, const float* o) { st4(p, make_float4(o[0], o[1], o[2], o[3])); }
+};
+template <typename T> struct LoadVec<T, 1> {
+  static __device__ __forceinline__ void ld(const T* p, float* o) { o[0] = Elem<T>::ld(p); }
+  static __device__ __forceinline__ void st(T* p, const float* o) { Elem<T>::st(p, o[0]); }
+};
+
+// sum and sum of squares of (x - pivot), pivot = row 0 (kills the cancellation in E[x^2]-E[x]^2)
+template <typename T, int VEC> struct StatsF {
+  static constexpr bool kTwo = true;
+  const T* x; int C;
+  __device__ __forceinline__ void eval(int64_t r, int c0, float* a, float* b) const {
+    float v[VEC], p[VEC];
+    LoadVec<T, VEC>::ld(x + r * C + c0, v);
+    LoadVec<T, VEC>::ld(x + c0, p);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) { float d = v[i] - p[i]; a[i] = d; b[i] = d * d; }
+  }
+};
+template <typename T, int VEC> struct SumF {
+  static constexpr bool kTwo = false;
+  const T* x; int C;
+  __device__ __forceinline__ void eval(int64_t r, int c0, float* a, float* b) const {
+    LoadVec<T, VEC>::ld(x + r * C + c0, a);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) b[i] = 0.f;
+  }
+};
+// BN backward sums: d = dout * (y > 0 ? 1 : leak), a = d, b = d * xhat
+template <typename T, int VEC> struct BnBwdF {
+  static constexpr bool kTwo = true;
+  const T* x; const T* dout; const float* mean; const float* invstd; const float* gamma; const float* beta;
+  float leak; int C;
+  __device__ __forceinline__ void eval(int64_t r, int c0, float* a, float* b) const {
+    float v[VEC], d[VEC];
+    LoadVec<T, VEC>::ld(x + r * C + c0, v);
+    LoadVec<T, VEC>::ld(dout + r * C + c0, d);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+      int c = c0 + i;
+      float xh = (v[i] - mean[c]) * invstd[c];
+      float y = xh * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+      float dd = (leak != 1.f && !(y > 0.f)) ? d[i] * leak : d[i];
+      a[i] = dd;
+      b[i] = dd * xh;
+    }
+  }
+};
+
+template <typename T>
+__global__ void k_bn_finalize(const double* __restrict__ acc, const T* __restrict__ x, int64_t n, int C, int training,
+                              float eps, float momentum, float* running_mean, float* running_var,
+                              float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (training) {
+    double mean = 0.0, var = 0.0;
+    if (n > 0) {
+      double pivot = (double)Elem<T>::ld(x + c);
+      double s1 = acc[c] / (double)n, s2 = acc[C + c] / (double)n;
+      mean = pivot + s1;
+      var = s2 - s1 * s1;
+      if (var < 0.0) var = 0.0;
+    }
+    double unbiased = var * (double)n / (double)(n > 1 ? n - 1 : 1);   // divisor max(N-1, 1)
+    running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
+    running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * unbiased);
+    save_mean[c] = (float)mean;
+    save_invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  } else {
+    save_mean[c] = running_mean[c];
+    save_invstd[c] = (float)(1.0 / sqrt((double)running_var[c] + (double)eps));
+  }
+}
+
+template <typename T, int VEC>
+__global__ void k_bn_apply(const T* __restrict__ x, int64_t nvec, int C, const float* __restrict__ mean,
+                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                           const float* __restrict__ beta, float leak, T* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  int c0 = (int)((i * VEC) % C);
+  float v[VEC];
+  LoadVec<T, VEC>::ld(x + i * VEC, v);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    int c = c0 + k;
+    float y = (v[k] - mean[c]) * invstd[c] * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+    v[k] = (leak != 1.f && !(y > 0.f)) ? y * leak : y;
+  }
+  LoadVec<T, VEC>::st(out + i * VEC, v);
+}
+
+template <typename T, int VEC>
+__global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dout, int64_t nvec, int C, int64_t n,
+                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                               const float* __restrict__ gamma, const float* __restrict__ beta, float leak,
+                               int training, const double* __restrict__ acc, T* __restrict__ dx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  int c0 = (int)((i * VEC) % C);
+  float v[VEC], d[VEC];
+  LoadVec<T, VEC>::ld(x + i * VEC, v);
+  LoadVec<T, VEC>::ld(dout + i * VEC, d);
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    int c = c0 + k;
+    float g = gamma ? gamma[c] : 1.f;
+    float xh = (v[k] - mean[c]) * invstd[c];
+    float y = xh * g + (beta ? beta[c] : 0.f);
+    float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+    float r = dd;
+    if (training) r = dd - (float)acc[c] * inv_n - xh * (float)acc[C + c] * inv_n;
+    v[k] = g * invstd[c] * r;
+  }
+  LoadVec<T, VEC>::st(dx + i * VEC, v);
+}
+
+__global__ void k_acc_to_float(const double* __restrict__ acc, int C, float* dgamma, float* dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] = (float)acc[c];
+  if (dgamma) dgamma[c] = (float)acc[C + c];
+}
+
+template <typename T, int VEC>
+__global__ void k_leaky_fwd(const T* __restrict__ x, int64_t nvec, float leak, T* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float v[VEC];
+  LoadVec<T, VEC>::ld(x + i * VEC, v);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) v[k] = v[k] > 0.f ? v[k] : v[k] * leak;
+  LoadVec<T, VEC>::st(out + i * VEC, v);
+}
+template <typename T, int VEC>
+__global__ void k_leaky_bwd(const T* __restrict__ x, const T* __restrict__ dout, int64_t nvec, float leak,
+                            T* __restrict__ dx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float v[VEC], d[VEC];
+  LoadVec<T, VEC>::ld(x + i * VEC, v);
+  LoadVec<T, VEC>::ld(dout + i * VEC, d);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) d[k] = v[k] > 0.f ? d[k] : d[k] * leak;
+  LoadVec<T, VEC>::st(dx + i * VEC, d);
+}
+template <typename T, int VEC>
+__global__ void k_add_fwd(const T* __restrict__ a, const T* __restrict__ b, int64_t nvec, float leak,
+                          T* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= nvec) return;
+  float v[VEC], w[VEC];
+  LoadVec<T, VEC>::ld(a + i * VEC, v);
+  LoadVec<T, VEC>::ld(b + i * VEC, w);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    float s = v[k] + w[k];
+    v[k] = (leak != 1.f && !(s > 0.f)) ? s * leak : s;
+  }
+  LoadVec<T, VEC>::st(out + i * VEC, v);
+}
+
+__global__ void k_input_scatter(const float* __restrict__ in, const int32_t* __restrict__ rows, int64_t n_in, int C,
+                                float* __restrict__ out, float* __restrict__ cnt) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_in * C) return;
+  int64_t r = i / C;
+  int c = (int)(i - r * C);
+  atomicAdd(out + (int64_t)rows[r] * C + c, in[i]);
+  if (cnt && c == 0) atomicAdd(cnt + rows[r], 1.f);
+}
+__global__ void k_div_rows(float* __restrict__ out, const float* __restrict__ cnt, int64_t n, int C) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  out[i] /= cnt[i / C];
+}
+template <typename TI, typename TO>
+__global__ void k_convert(const TI* __restrict__ in, int64_t n, TO* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) Elem<TO>::st(out + i, Elem<TI>::ld(in + i));
+}
+template <typename TI, typename TO>
+__global__ void k_rows_gather(const TI* __restrict__ src, const int32_t* __restrict__ rows, int64_t n_rows, int C,
+                              TO* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rows * C) return;
+  int64_t r = i / C;
+  int c = (int)(i - r * C);
+  Elem<TO>::st(out + i, Elem<TI>::ld(src + (int64_t)rows[r] * C + c));
+}
+template <typename TI>
+__global__ void k_rows_scatter_add(const TI* __restrict__ src, const int32_t* __restrict__ rows, int64_t n_rows, int C,
+                                   float* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rows * C) return;
+  int64_t r = i / C;
+  int c = (int)(i - r * C);
+  atomicAdd(out + (int64_t)rows[r] * C + c, Elem<TI>::ld(src + i));
+}
+
+template <typename T>
+__global__ void k_s2d_fwd(const T* __restrict__ x, const uint64_t* __restrict__ keys, int64_t n, int C, int s0, int s1,
+                          int s2, float* __restrict__ dense) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  int64_t r = i / C;
+  int c = (int)(i - r * C);
+  int x0, x1, x2, b;
+  key_unpack(keys[r], x0, x1, x2, b);
+  if (x0 >= s0 || x1 >= s1 || x2 >= s2) return;
+  dense[((((int64_t)b * C + c) * s0 + x0) * s1 + x1) * s2 + x2] = Elem<T>::ld(x + i);
+}
+template <typename T>
+__global__ void k_s2d_bwd(const float* __restrict__ ddense, const uint64_t* __restrict__ keys, int64_t n, int C, int s0,
+                          int s1, int s2, T* __restrict__ dx) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n * C) return;
+  int64_t r = i / C;
+  int c = (int)(i - r * C);
+  int x0, x1, x2, b;
+  key_unpack(keys[r], x0, x1, x2, b);
+  float v = 0.f;
+  if (x0 < s0 && x1 < s1 && x2 < s2) v = ddense[((((int64_t)b * C + c) * s0 + x0) * s1 + x1) * s2 + x2];
+  Elem<T>::st(dx + i, v);
+}
+
+template <int VEC, typename F>
+int launch_col_reduce(F f, int64_t n, int C, double* acc, cudaStream_t s) {
+  int CV = C / VEC;
+  if (CV > kRedThreads) return SCN_ERR_UNSUPPORTED;
+  int RY = kRedThreads / CV;
+  size_t smem = (size_t)RY * CV * 2 * VEC * sizeof(float);
+  unsigned g = (unsigned)((n + kRedRows - 1) / kRedRows);
+  k_col_reduce2<VEC, F><<<g, kRedThreads, smem, s>>>(f, n, C, acc);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+template <typename T>
+int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* beta, float* rm, float* rv,
+                 int training, float eps, float momentum, float leak, float* save_mean, float* save_invstd,
+                 double* ws, T* out, cudaStream_t s) {
+  const bool vec = (C % 4) == 0;
+  if (training) {
+    SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
+    if (n > 0) {
+      int rc = vec ? launch_col_reduce<4>(StatsF<T, 4>{x, C}, n, C, ws, s)
+                   : launch_col_reduce<1>(StatsF<T, 1>{x, C}, n, C, ws, s);
+      if (rc) return rc;
+    }
+  }
+  k_bn_finalize<T><<<grid_for(C, 128), 128, 0, s>>>(ws, x, n, C, training, eps, momentum, rm, rv, save_mean,
+                                                    save_invstd);
+  SCN_LAUNCH_CHECK();
+  if (n == 0) return SCN_OK;
+  int64_t total = n * C;
+  if (vec)
+    k_bn_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, total / 4, C, save_mean, save_invstd, gamma, beta,
+                                                              leak, out);
+  else
+    k_bn_apply<T, 1><<<grid_for(total, 256), 256, 0, s>>>(x, total, C, save_mean, save_invstd, gamma, beta, leak, out);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+template <typename T>
+int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamma, const float* beta,
+                  const float* mean, const float* invstd, int training, float leak, double* ws, T* dx, float* dgamma,
+                  float* dbeta, cudaStream_t s) {
+  const bool vec = (C % 4) == 0;
+  SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
+  if (n > 0) {
+    int rc = vec ? launch_col_reduce<4>(BnBwdF<T, 4>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s)
+                 : launch_col_reduce<1>(BnBwdF<T, 1>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s);
+    if (rc) return rc;
+  }
+  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta);
+  SCN_LAUNCH_CHECK();
+  if (n == 0) return SCN_OK;
+  int64_t total = n * C;
+  if (vec)
+    k_bn_bwd_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, dout, total / 4, C, n, mean, invstd, gamma, beta,
+                                                                  leak, training, ws, dx);
+  else
+    k_bn_bwd_apply<T, 1><<<grid_for(total, 256), 256, 0, s>>>(x, dout, total, C, n, mean, invstd, gamma, beta, leak,
+                                                              training, ws, dx);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+#define DISPATCH_T(dtype, CALL_F32, CALL_BF16)          \
+  switch (dtype) {                                      \
+    case SCN_F32: { CALL_F32; break; }                  \
+    case SCN_BF16: { CALL_BF16; break; }                \
+    default: return SCN_ERR_ARG;                        \
+  }
+
+template <typename T>
+int ew_launch3(int which, const T* a, const T* b, int64_t count, float leak, T* out, cudaStream_t s) {
+  if (count == 0) return SCN_OK;
+  bool vec = (count % 4 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
+  int64_t nv = vec ? count / 4 : count;
+  unsigned g = grid_for(nv, 256);
+  if (which == 0) {
+    if (vec) k_leaky_fwd<T, 4><<<g, 256, 0, s>>>(a, nv, leak, out); else k_leaky_fwd<T, 1><<<g, 256, 0, s>>>(a, nv, leak, out);
+  } else if (which == 1) {
+    if (vec) k_leaky_bwd<T, 4><<<g, 256, 0, s>>>(a, b, nv, leak, out); else k_leaky_bwd<T, 1><<<g, 256, 0, s>>>(a, b, nv, leak, out);
+  } else {
+    if (vec) k_add_fwd<T, 4><<<g, 256, 0, s>>>(a, b, nv, leak, out); else k_add_fwd<T, 1><<<g, 256, 0, s>>>(a, b, nv, leak, out);
+  }
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+}  // namespace
+
+extern "C" int scn_bn_forward(const void* x, int dtype, int64_t n, int C, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, int training, float eps, float momentum,
+                              float leakiness, float* save_mean, float* save_invstd, double* stats_ws, void* out,
+                              void* stream) {
+  if (C < 1 || !running_mean || !running_var || !save_mean || !save_invstd || !stats_ws) return SCN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_T(dtype,
+             return bn_forward_t<float>((const float*)x, n, C, gamma, beta, running_mean, running_var, training, eps,
+                                        momentum, leakiness, save_mean, save_invstd, stats_ws, (float*)out, s),
+             return bn_forward_t<__nv_bfloat16>((const __nv_bfloat16*)x, n, C, gamma, beta, running_mean, running_var,
+                                                training, eps, momentum, leakiness, save_mean, save_invstd, stats_ws,
+                                                (__nv_bfloat16*)out, s));
+  return SCN_OK;
+}
+
+extern "C" int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd, int training,
+                               float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta, void* stream) {
+  if (C < 1 || !save_mean || !save_invstd || !stats_ws) return SCN_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_T(dtype,
+             return bn_backward_t<float>((const float*)x, (const float*)dout, n, C, gamma, beta, save_mean, save_invstd,
+                                         training, leakiness, stats_ws, (float*)dx, dgamma, dbeta, s),
+             return bn_backward_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, n, C, gamma, beta,
+                                                 save_mean, save_invstd, training, leakiness, stats_ws,
+                                                 (__nv_bfloat16*)dx, dgamma, dbeta, s));
+  return SCN_OK;
+}
+
+extern "C" int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (C < 1 || !out || !stats_ws) return SCN_ERR_ARG;
+  double* acc = stats_ws;
+  SCN_CUDA(cudaMemsetAsync(acc, 0, 2 * (size_t)C * sizeof(double), s));
+  int rc = SCN_OK;
+  if (n > 0) {
+    const bool vec = (C % 4) == 0;
+    if (dtype == SCN_F32)
+      rc = vec ? launch_col_reduce<4>(SumF<float, 4>{(const float*)x, C}, n, C, acc, s)
+               : launch_col_reduce<1>(SumF<float, 1>{(const float*)x, C}, n, C, acc, s);
+    else if (dtype == SCN_BF16)
+      rc = vec ? launch_col_reduce<4>(SumF<__nv_bfloat16, 4>{(const __nv_bfloat16*)x, C}, n, C, acc, s)
+               : launch_col_reduce<1>(SumF<__nv_bfloat16, 1>{(const __nv_bfloat16*)x, C}, n, C, acc, s);
+    else
+      rc = SCN_ERR_ARG;
+  }
+  if (rc != SCN_OK) return rc;
+  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(acc, C, nullptr, out);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+extern "C" int scn_leaky_forward(const void* x, int dtype, int64_t count, float leak, void* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return ew_launch3<float>(0, (const float*)x, nullptr, count, leak, (float*)out, s),
+             return ew_launch3<__nv_bfloat16>(0, (const __nv_bfloat16*)x, nullptr, count, leak, (__nv_bfloat16*)out, s));
+  return SCN_OK;
+}
+extern "C" int scn_leaky_backward(const void* x, const void* dout, int dtype, int64_t count, float leak, void* dx,
+                                  void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return ew_launch3<float>(1, (const float*)x, (const float*)dout, count, leak, (float*)dx, s),
+             return ew_launch3<__nv_bfloat16>(1, (const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, count, leak,
+                                              (__nv_bfloat16*)dx, s));
+  return SCN_OK;
+}
+extern "C" int scn_add_forward(const void* a, const void* b, int dtype, int64_t count, float leak, void* out,
+                               void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  DISPATCH_T(dtype, return ew_launch3<float>(2, (const float*)a, (const float*)b, count, leak, (float*)out, s),
+             return ew_launch3<__nv_bfloat16>(2, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, count, leak,
+                                              (__nv_bfloat16*)out, s));
+  return SCN_OK;
+}
+
+extern "C" int scn_input_layer_forward(const float* in, const int32_t* row_of_input, int64_t n_in, int64_t n_active,
+                                       int C, int mode, void* out, int out_dtype, float* count_ws, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mode == 1 || mode == 2) return SCN_ERR_UNSUPPORTED;   // last/first-wins: not used by the reference
+  if (out_dtype != SCN_F32) return SCN_ERR_UNSUPPORTED;     // accumulate in fp32; cast afterwards
+  if (n_active == 0) return SCN_OK;
+  if (!out || !in || !row_of_input) return SCN_ERR_ARG;
+  SCN_CUDA(cudaMemsetAsync(out, 0, (size_t)n_active * C * sizeof(float), s));
+  float* cnt = nullptr;
+  if (mode == 4) {
+    if (!count_ws) return SCN_ERR_WORKSPACE;
+    cnt = count_ws;
+    SCN_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n_active * sizeof(float), s));
+  }
+  k_input_scatter<<<grid_for(n_in * C, 256), 256, 0, s>>>(in, row_of_input, n_in, C, (float*)out, cnt);
+  SCN_LAUNCH_CHECK();
+  if (mode == 4) {
+    k_div_rows<<<grid_for(n_active * C, 256), 256, 0, s>>>((float*)out, cnt, n_active, C);
+    SCN_LAUNCH_CHECK();
+  }
+  return SCN_OK;
+}
+
+extern "C" int scn_rows_gather(const void* src, int dtype, const int32_t* rows, int64_t n_rows, int C, void* out,
+                               int out_dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_rows == 0) return SCN_OK;
+  unsigned g = grid_for(n_rows * C, 256);
+  if (rows == nullptr) {   // plain dtype conversion of a [n_rows, C] matrix
+    int64_t n = n_rows * C;
+    if (dtype == SCN_F32 && out_dtype == SCN_BF16) k_convert<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)src, n, (__nv_bfloat16*)out);
+    else if (dtype == SCN_BF16 && out_dtype == SCN_F32) k_convert<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, n, (float*)out);
+    else if (dtype == SCN_F32 && out_dtype == SCN_F32) k_convert<float, float><<<g, 256, 0, s>>>((const float*)src, n, (float*)out);
+    else if (dtype == SCN_BF16 && out_dtype == SCN_BF16) k_convert<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, n, (__nv_bfloat16*)out);
+    else return SCN_ERR_ARG;
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
+  if (dtype == SCN_F32 && out_dtype == SCN_F32) k_rows_gather<float, float><<<g, 256, 0, s>>>((const float*)src, rows, n_rows, C, (float*)out);
+  else if (dtype == SCN_F32 && out_dtype == SCN_BF16) k_rows_gather<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)src, rows, n_rows, C, (__nv_bfloat16*)out);
+  else if (dtype == SCN_BF16 && out_dtype == SCN_F32) k_rows_gather<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, rows, n_rows, C, (float*)out);
+  else if (dtype == SCN_BF16 && out_dtype == SCN_BF16) k_rows_gather<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, rows, n_rows, C, (__nv_bfloat16*)out);
+  else return SCN_ERR_ARG;
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+extern "C" int scn_rows_scatter_add(const void* src, int dtype, const int32_t* rows, int64_t n_rows, int C,
+                                    float* out_f32, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_rows == 0) return SCN_OK;
+  if (!src || !rows || !out_f32) return SCN_ERR_ARG;
+  unsigned g = grid_for(n_rows * C, 256);
+  if (dtype == SCN_F32) k_rows_scatter_add<float><<<g, 256, 0, s>>>((const float*)src, rows, n_rows, C, out_f32);
+  else if (dtype == SCN_BF16) k_rows_scatter_add<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, rows, n_rows, C, out_f32);
+  else return SCN_ERR_ARG;
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+extern "C" int scn_sparse_to_dense_forward(const void* x, int dtype, const uint64_t* keys, int64_t n, int C, int batch,
+                                           int s0, int s1, int s2, float* dense, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t total = (size_t)batch * C * s0 * s1 * s2;
+  if (total == 0) return SCN_OK;
+  if (!dense) return SCN_ERR_ARG;
+  SCN_CUDA(cudaMemsetAsync(dense, 0, total * sizeof(float), s));
+  if (n == 0) return SCN_OK;
+  unsigned g = grid_for(n * C, 256);
+  if (dtype == SCN_F32) k_s2d_fwd<float><<<g, 256, 0, s>>>((const float*)x, keys, n, C, s0, s1, s2, dense);
+  else if (dtype == SCN_BF16) k_s2d_fwd<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, keys, n, C, s0, s1, s2, dense);
+  else return SCN_ERR_ARG;
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+extern "C" int scn_sparse_to_dense_backward(const float* ddense, const uint64_t* keys, int64_t n, int C, int batch,
+                                            int s0, int s1, int s2, void* dx, int dtype, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  (void)batch;
+  if (n == 0) return SCN_OK;
+  unsigned g = grid_for(n * C, 256);
+  if (dtype == SCN_F32) k_s2d_bwd<float><<<g, 256, 0, s>>>(ddense, keys, n, C, s0, s1, s2, (float*)dx);
+  else if (dtype == SCN_BF16) k_s2d_bwd<__nv_bfloat16><<<g, 256, 0, s>>>(ddense, keys, n, C, s0, s1, s2, (__nv_bfloat16*)dx);
+  else return SCN_ERR_ARG;
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}

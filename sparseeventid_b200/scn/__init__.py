@@ -1,0 +1,13 @@
+"""B200-native implementation of the ``sparseconvnet`` module surface (see modules.py)."""
+from .config import feature_dtype, get_precision, set_precision
+from .core import Metadata, SparseConvNetTensor
+from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, Convolution, Deconvolution,
+                      Identity, InputLayer, LeakyReLU, OutputLayer, ReLU, Sequential, Sigmoid, SparseToDense,
+                      SubmanifoldConvolution, Tanh)
+
+__all__ = [
+    "AddTable", "BatchNormalization", "BatchNormLeakyReLU", "BatchNormReLU", "Convolution", "Deconvolution",
+    "Identity", "InputLayer", "LeakyReLU", "OutputLayer", "ReLU", "Sequential", "Sigmoid", "SparseToDense",
+    "SubmanifoldConvolution", "Tanh", "SparseConvNetTensor", "Metadata", "set_precision", "get_precision",
+    "feature_dtype",
+]

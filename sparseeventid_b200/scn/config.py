@@ -1,0 +1,38 @@
+"""Numerics mode of the sparse-convolution path.
+
+  "fp32"  : fp32 features, exact fp32 FMA convolutions (parity mode; SCN itself is fp32,
+            SURVEY.md App. C).
+  "mixed" : fp32 features in HBM, bf16 tensor-core operands, fp32 accumulate.
+  "bf16"  : bf16 features in HBM, bf16 tensor-core operands, fp32 accumulate; BatchNorm
+            statistics, parameters and parameter gradients stay fp32 (BASELINE.json config 3).
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from .._lib import PREC_BF16, PREC_FP32
+
+_MODES = ("fp32", "mixed", "bf16")
+_state = {"mode": os.environ.get("SCN_B200_PRECISION", "bf16")}
+if _state["mode"] not in _MODES:
+    raise ValueError(f"SCN_B200_PRECISION must be one of {_MODES}")
+
+
+def set_precision(mode: str) -> None:
+    if mode not in _MODES:
+        raise ValueError(f"precision must be one of {_MODES}, got {mode!r}")
+    _state["mode"] = mode
+
+
+def get_precision() -> str:
+    return _state["mode"]
+
+
+def feature_dtype() -> torch.dtype:
+    return torch.bfloat16 if _state["mode"] == "bf16" else torch.float32
+
+
+def precision_code() -> int:
+    return PREC_FP32 if _state["mode"] == "fp32" else PREC_BF16

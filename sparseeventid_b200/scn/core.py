@@ -1,0 +1,175 @@
+"""SparseConvNetTensor + device-resident Metadata (SURVEY.md App. A.1, §8b "Ownership").
+
+SCN keeps per-sample sparsehash grids and vectors of rule vectors on the host; here one
+Metadata object owns, per spatial size, the packed site keys in row order plus one open-
+addressing hash table, and caches one neighbour table per (spatial size, filter[, stride]).
+It is shared by reference by every tensor derived from one InputLayer call.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Tuple
+
+import torch
+
+from . import ops
+
+
+def as_tuple(v, dimension: int) -> Tuple[int, ...]:
+    """SCN accepts int / list / tuple / tensor for sizes (reference src/networks/resnet.py:26-36)."""
+    if isinstance(v, torch.Tensor):
+        v = v.tolist()
+    if hasattr(v, "tolist"):
+        v = v.tolist()
+    if isinstance(v, int):
+        return tuple(v for _ in range(dimension))
+    v = tuple(int(x) for x in v)
+    if len(v) != dimension:
+        raise ValueError(f"expected {dimension} values, got {v}")
+    return v
+
+
+def pad3(t: Tuple[int, ...], fill: int) -> Tuple[int, int, int]:
+    return tuple(t) + (fill,) * (3 - len(t))
+
+
+@dataclass
+class Level:
+    keys: torch.Tensor          # int64 [n]: packed (batch|x0|x1|x2) in row order
+    n: int
+    table_keys: torch.Tensor
+    table_vals: torch.Tensor
+    cap: int
+
+    @property
+    def n_pad(self):
+        return ops.pad128(self.n)
+
+
+@dataclass
+class StridedRule:
+    out_spatial: Tuple[int, ...]
+    down: torch.Tensor          # [K, n_out_pad]
+    up: torch.Tensor            # [K, n_in_pad]
+    K: int
+    n_in: int
+    n_out: int
+
+
+class Metadata:
+    def __init__(self, dimension: int, device):
+        self.dimension = dimension
+        self.device = device
+        self.levels: Dict[Tuple[int, ...], Level] = {}
+        self.subm: Dict[tuple, torch.Tensor] = {}
+        self.strided: Dict[tuple, StridedRule] = {}
+        self.row_of_input = None        # int32 [n_input]
+        self.n_input = 0
+        self.batch_size = 0
+        self.input_spatial = None
+
+    # -- levels ------------------------------------------------------------------------------
+    def add_level(self, spatial, keys, table=None):
+        n = int(keys.shape[0])
+        if table is None:
+            table = ops.hash_build(keys)
+        self.levels[tuple(spatial)] = Level(keys, n, table[0], table[1], table[2])
+        return self.levels[tuple(spatial)]
+
+    def coords(self, spatial) -> torch.Tensor:
+        """int64 [n, dimension+1] (coords..., batch) in row order == get_spatial_locations()."""
+        lvl = self.levels[tuple(spatial)]
+        c = ops.unpack_keys(lvl.keys).long()
+        if self.dimension < 3:
+            c = torch.cat([c[:, : self.dimension], c[:, 3:4]], 1)
+        return c
+
+    # -- rulebooks ---------------------------------------------------------------------------
+    def subm_table(self, spatial, filt) -> torch.Tensor:
+        key = (tuple(spatial), tuple(filt))
+        if key not in self.subm:
+            lvl = self.levels[tuple(spatial)]
+            self.subm[key] = ops.subm_rulebook(lvl.keys, lvl.table_keys, lvl.table_vals, lvl.cap, pad3(filt, 1))
+        return self.subm[key]
+
+    def strided_rule(self, spatial, filt, stride) -> StridedRule:
+        spatial, filt, stride = tuple(spatial), tuple(filt), tuple(stride)
+        key = (spatial, filt, stride)
+        if key in self.strided:
+            return self.strided[key]
+        if filt != stride:
+            raise NotImplementedError(
+                "strided Convolution/Deconvolution is implemented for filter_size == filter_stride "
+                "(every use in the reference: [2,2,2], [1,2,2], 2)")
+        out_spatial = []
+        for a in range(len(spatial)):
+            if (spatial[a] - filt[a]) % stride[a] != 0:
+                raise AssertionError(f"spatial size {spatial} not compatible with filter {filt} / stride {stride}")
+            out_spatial.append((spatial[a] - filt[a]) // stride[a] + 1)
+        out_spatial = tuple(out_spatial)
+        lvl = self.levels[spatial]
+        keys_out, out_row, off = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
+        if out_spatial in self.levels:
+            # coarse grid already exists (e.g. built through another path): re-index onto its rows
+            have = self.levels[out_spatial]
+            remap = ops.hash_lookup(keys_out, have.table_keys, have.table_vals, have.cap)
+            out_row = remap[out_row.long()].contiguous()
+            n_out = have.n
+        else:
+            self.add_level(out_spatial, keys_out.clone())
+            n_out = int(keys_out.shape[0])
+        K = 1
+        for f in filt:
+            K *= f
+        down, up = ops.strided_tables(out_row, off, K, lvl.n, n_out)
+        rule = StridedRule(out_spatial, down, up, K, lvl.n, n_out)
+        self.strided[key] = rule
+        return rule
+
+
+class SparseConvNetTensor:
+    """features [nActive, C] + shared metadata + spatial_size (LongTensor), as in SCN."""
+
+    def __init__(self, features=None, metadata=None, spatial_size=None):
+        self.features = features
+        self.metadata = metadata
+        self.spatial_size = spatial_size
+
+    def _sp(self):
+        return tuple(int(v) for v in self.spatial_size)
+
+    def get_spatial_locations(self, spatial_size=None):
+        sp = self._sp() if spatial_size is None else tuple(int(v) for v in spatial_size)
+        return self.metadata.coords(sp).cpu()
+
+    def batch_size(self):
+        return self.metadata.batch_size
+
+    def to(self, *args, **kwargs):
+        self.features = self.features.to(*args, **kwargs)
+        return self
+
+    def type(self, t=None):
+        if t is None:
+            return self.features.type()
+        self.features = self.features.type(t)
+        return self
+
+    def cuda(self):
+        self.features = self.features.cuda()
+        return self
+
+    def cpu(self):
+        out = SparseConvNetTensor(self.features.cpu(), self.metadata, self.spatial_size)
+        return out
+
+    def detach(self):
+        return SparseConvNetTensor(self.features.detach(), self.metadata, self.spatial_size)
+
+    @property
+    def requires_grad(self):
+        return self.features.requires_grad
+
+    def __repr__(self):
+        return (f"SparseConvNetTensor<b200>(features={tuple(self.features.shape)}, dtype={self.features.dtype}, "
+                f"spatial_size={self._sp()})")

@@ -1,0 +1,279 @@
+"""nn.Module surface of ``sparseconvnet`` used by the reference, B200-backed.
+
+Constructor forms, parameter/buffer names, shapes and initialisation follow SCN (SURVEY.md
+App. A) so the reference's ``src/networks/*.py`` run unchanged and checkpoints round-trip.
+Every forward runs hand-written sm_100a kernels through libscn_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+from .. import _lib as L
+from . import config, ops
+from . import functional as F
+from .core import Metadata, SparseConvNetTensor, as_tuple
+
+
+def _volume(t):
+    v = 1
+    for x in t:
+        v *= x
+    return v
+
+
+def _new_like(input, features, spatial_size=None):
+    return SparseConvNetTensor(features, input.metadata, input.spatial_size if spatial_size is None else spatial_size)
+
+
+class InputLayer(nn.Module):
+    """scn.InputLayer(dimension, spatial_size, mode=3)  -- reference src/networks/resnet.py:26-29,40-43.
+
+    forward((coords, features[, batch_size])): coords [N, dimension(+1)] of any dtype, batch index
+    in the LAST column (src/io/data_transforms.py:43-46,242); features [N, C].
+    mode 0: no duplicates promised, 3: sum duplicates (default), 4: mean.  (1/2 = last/first wins
+    are not implemented on the GPU; the reference never selects them.)
+    """
+
+    def __init__(self, dimension, spatial_size, mode=3):
+        super().__init__()
+        self.dimension = dimension
+        self.spatial_size = torch.LongTensor(list(as_tuple(spatial_size, dimension)))
+        self.mode = mode
+
+    def forward(self, input):
+        coords, feats = input[0], input[1]
+        batch_size = int(input[2]) if len(input) > 2 and input[2] is not None else 0
+        coords = torch.as_tensor(coords)
+        feats = torch.as_tensor(feats)
+        L.require_cuda(feats, "InputLayer(features)")
+        if not coords.is_cuda:
+            coords = coords.to(feats.device, non_blocking=True)
+        if coords.dim() != 2 or coords.shape[1] not in (self.dimension, self.dimension + 1):
+            raise ValueError(f"coords must be [N, {self.dimension}] or [N, {self.dimension + 1}]")
+        md = Metadata(self.dimension, feats.device)
+        keys = ops.pack_coords(coords, self.dimension)
+        rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
+        sp = tuple(int(v) for v in self.spatial_size)
+        lvl = md.add_level(sp, keys_out, (tk, tv, cap))
+        md.row_of_input = rows
+        md.n_input = int(keys.shape[0])
+        md.input_spatial = sp
+        if lvl.n > 0:
+            max_b = int((keys_out.max() >> 48).item())
+            md.batch_size = max(batch_size, max_b + 1)
+        else:
+            md.batch_size = batch_size
+        out = SparseConvNetTensor(None, md, self.spatial_size)
+        out.features = F.InputLayerFn.apply(feats, rows, lvl.n, self.mode)
+        return out
+
+    def __repr__(self):
+        return f"InputLayer(dimension={self.dimension}, spatial_size={self.spatial_size.tolist()}, mode={self.mode})"
+
+
+class OutputLayer(nn.Module):
+    """scn.OutputLayer(dimension): features back in the original input-row order (App. A.7)."""
+
+    def __init__(self, dimension):
+        super().__init__()
+        self.dimension = dimension
+
+    def forward(self, input):
+        return F.OutputLayerFn.apply(input.features, input.metadata.row_of_input)
+
+
+class _ConvBase(nn.Module):
+    def _init_params(self, nIn, nOut, bias):
+        k = self.filter_volume
+        w = torch.empty(k, 1, nIn, nOut)
+        w.normal_(0, math.sqrt(2.0 / (nIn * k)))
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # accept SCN 2018-19 checkpoints whose conv weights are [K, Cin, Cout]
+        key = prefix + "weight"
+        if key in state_dict and state_dict[key].dim() == 3:
+            w = state_dict[key]
+            state_dict[key] = w.reshape(w.shape[0], 1, w.shape[1], w.shape[2])
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def _check(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, \
+            f"expected {self.nIn} input planes, got {input.features.size(1)}"
+
+
+class SubmanifoldConvolution(_ConvBase):
+    """scn.SubmanifoldConvolution(dimension, nIn, nOut, filter_size, bias, groups=1)
+    -- reference src/networks/sparse_building_blocks.py:29-34, src/networks/resnet.py:30-36,44-50,105-110."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
+        super().__init__()
+        assert groups == 1, "groups > 1 is not used by the reference"
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = as_tuple(filter_size, dimension)
+        assert all(f % 2 == 1 for f in self.filter_size), "submanifold filters must be odd"
+        self.filter_volume = _volume(self.filter_size)
+        self._init_params(nIn, nOut, bias)
+
+    def forward(self, input):
+        self._check(input)
+        md = input.metadata
+        nbr = md.subm_table(input._sp(), self.filter_size)
+        n = md.levels[input._sp()].n
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, nbr, nbr, n, True)
+        return _new_like(input, feats)
+
+    def __repr__(self):
+        return f"SubmanifoldConvolution {self.nIn}->{self.nOut} C{list(self.filter_size)}"
+
+
+class Convolution(_ConvBase):
+    """scn.Convolution(dimension, nIn, nOut, filter_size, filter_stride, bias)
+    -- reference src/networks/sparse_building_blocks.py:110-117."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        assert groups == 1
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = as_tuple(filter_size, dimension)
+        self.filter_stride = as_tuple(filter_stride, dimension)
+        self.filter_volume = _volume(self.filter_size)
+        self._init_params(nIn, nOut, bias)
+
+    def forward(self, input):
+        self._check(input)
+        md = input.metadata
+        rule = md.strided_rule(input._sp(), self.filter_size, self.filter_stride)
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.down, rule.up, rule.n_out, False)
+        return _new_like(input, feats, torch.LongTensor(list(rule.out_spatial)))
+
+    def __repr__(self):
+        return f"Convolution {self.nIn}->{self.nOut} C{list(self.filter_size)}/{list(self.filter_stride)}"
+
+
+class Deconvolution(_ConvBase):
+    """scn.Deconvolution(dimension, nIn, nOut, filter_size, filter_stride, bias)
+    -- reference src/networks/sparse_building_blocks.py:207-213.  The fine grid must already exist
+    in the metadata (App. A.7)."""
+
+    def __init__(self, dimension, nIn, nOut, filter_size, filter_stride, bias, groups=1):
+        super().__init__()
+        assert groups == 1
+        self.dimension, self.nIn, self.nOut = dimension, nIn, nOut
+        self.filter_size = as_tuple(filter_size, dimension)
+        self.filter_stride = as_tuple(filter_stride, dimension)
+        self.filter_volume = _volume(self.filter_size)
+        self._init_params(nIn, nOut, bias)
+
+    def forward(self, input):
+        self._check(input)
+        md = input.metadata
+        sp = input._sp()
+        fine = tuple((sp[a] - 1) * self.filter_stride[a] + self.filter_size[a] for a in range(self.dimension))
+        if fine not in md.levels:
+            raise RuntimeError("Deconvolution needs the fine grid to exist in the metadata")
+        rule = md.strided_rule(fine, self.filter_size, self.filter_stride)
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.up, rule.down, rule.n_in, False)
+        return _new_like(input, feats, torch.LongTensor(list(fine)))
+
+
+class BatchNormalization(nn.Module):
+    """scn.BatchNormalization(nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1)
+    -- reference src/networks/sparse_building_blocks.py:39,122.  SCN conventions (App. A.5)."""
+
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1):
+        super().__init__()
+        self.nPlanes, self.eps, self.momentum, self.affine, self.leakiness = nPlanes, eps, momentum, affine, leakiness
+        self.register_buffer("running_mean", torch.zeros(nPlanes))
+        self.register_buffer("running_var", torch.ones(nPlanes))
+        if affine:
+            self.weight = nn.Parameter(torch.ones(nPlanes))
+            self.bias = nn.Parameter(torch.zeros(nPlanes))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, input):
+        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
+        feats = F.BatchNormFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
+                                    self.training, float(self.eps), float(self.momentum), float(self.leakiness))
+        return _new_like(input, feats)
+
+    def __repr__(self):
+        return (f"BatchNorm({self.nPlanes},eps={self.eps},momentum={self.momentum},affine={self.affine}"
+                f",leakiness={self.leakiness})")
+
+
+class BatchNormReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9):
+        super().__init__(nPlanes, eps, momentum, True, 0)
+
+
+class BatchNormLeakyReLU(BatchNormalization):
+    def __init__(self, nPlanes, eps=1e-4, momentum=0.9, leakiness=0.333):
+        super().__init__(nPlanes, eps, momentum, True, leakiness)
+
+
+class LeakyReLU(nn.Module):
+    """scn.LeakyReLU(leak=1/3) -- reference sparse_building_blocks.py:20,45,80,128."""
+
+    def __init__(self, leak=1.0 / 3.0):
+        super().__init__()
+        self.leak = leak
+
+    def forward(self, input):
+        return _new_like(input, F.LeakyReLUFn.apply(input.features, float(self.leak)))
+
+
+class ReLU(LeakyReLU):
+    def __init__(self):
+        super().__init__(0.0)
+
+
+class Tanh(nn.Module):
+    def forward(self, input):
+        return _new_like(input, torch.tanh(input.features))
+
+
+class Sigmoid(nn.Module):
+    def forward(self, input):
+        return _new_like(input, torch.sigmoid(input.features))
+
+
+class Identity(nn.Module):
+    def forward(self, input):
+        return input
+
+
+class AddTable(nn.Module):
+    """scn.AddTable(): features = sum of the list's features (rows aligned) -- sparse_building_blocks.py:82,96."""
+
+    def forward(self, input):
+        feats = input[0].features
+        for t in input[1:]:
+            feats = F.AddFn.apply(feats, t.features)
+        return _new_like(input[0], feats)
+
+
+class SparseToDense(nn.Module):
+    """scn.SparseToDense(dimension, nPlanes) -> dense [B, C, *spatial] fp32 -- src/networks/resnet.py:123-125."""
+
+    def __init__(self, dimension, nPlanes):
+        super().__init__()
+        self.dimension, self.nPlanes = dimension, nPlanes
+
+    def forward(self, input):
+        md = input.metadata
+        sp = input._sp()
+        lvl = md.levels[sp]
+        sp3 = tuple(sp) + (1,) * (3 - len(sp))
+        dense = F.SparseToDenseFn.apply(input.features, lvl.keys, md.batch_size, sp3)
+        return dense.view((md.batch_size, input.features.shape[1]) + tuple(sp))
+
+
+class Sequential(nn.Sequential):
+    pass

@@ -1,0 +1,282 @@
+"""Thin tensor-level wrappers over the C ABI (include/scn_b200.h).  No autograd here.
+
+Every function takes CUDA tensors, allocates outputs with torch's caching allocator on the
+current stream, and calls libscn_b200.so through ctypes.  Nothing here computes on the host.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib as L
+
+
+def _i32(n, device):
+    return torch.empty((n,), dtype=torch.int32, device=device)
+
+
+def pad128(n: int) -> int:
+    return (n + 127) // 128 * 128
+
+
+# ---------------------------------------------------------------------------- hash / rulebooks
+
+
+def pack_coords(coords: torch.Tensor, dimension: int) -> torch.Tensor:
+    L.require_cuda(coords, "pack_coords")
+    if coords.dtype not in L.COORD_CODES:
+        coords = coords.long()
+    coords = coords.contiguous()
+    n, ncols = coords.shape
+    keys = torch.empty((n,), dtype=torch.int64, device=coords.device)
+    L.check(L.lib().scn_pack_coords(L.ptr(coords), L.COORD_CODES[coords.dtype], n, ncols, dimension, L.ptr(keys),
+                                    L.stream()), "scn_pack_coords")
+    return keys
+
+
+def unpack_keys(keys: torch.Tensor) -> torch.Tensor:
+    n = keys.shape[0]
+    out = torch.empty((n, 4), dtype=torch.int32, device=keys.device)
+    L.check(L.lib().scn_unpack_keys(L.ptr(keys), n, L.ptr(out), L.stream()), "scn_unpack_keys")
+    return out
+
+
+def new_table(n: int, device):
+    cap = int(L.lib().scn_hash_capacity(n))
+    tk = torch.empty((cap,), dtype=torch.int64, device=device)
+    tv = torch.empty((cap,), dtype=torch.int32, device=device)
+    return tk, tv, cap
+
+
+def hash_build(keys: torch.Tensor):
+    n = keys.shape[0]
+    tk, tv, cap = new_table(n, keys.device)
+    L.check(L.lib().scn_hash_build(L.ptr(keys), n, L.ptr(tk), L.ptr(tv), cap, L.stream()), "scn_hash_build")
+    return tk, tv, cap
+
+
+def hash_lookup(queries: torch.Tensor, tk, tv, cap) -> torch.Tensor:
+    n = queries.shape[0]
+    out = _i32(n, queries.device)
+    L.check(L.lib().scn_hash_lookup(L.ptr(queries), n, L.ptr(tk), L.ptr(tv), cap, L.ptr(out), L.stream()),
+            "scn_hash_lookup")
+    return out
+
+
+def input_layer_rules(keys_in: torch.Tensor):
+    """-> (row_of_input int32 [n], keys_out int64 [n_active], table_keys, table_vals, cap).  One D2H sync."""
+    n = keys_in.shape[0]
+    dev = keys_in.device
+    tk, tv, cap = new_table(n, dev)
+    rows = _i32(n, dev)
+    keys_out = torch.empty((n,), dtype=torch.int64, device=dev)
+    n_active = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws_bytes = int(L.lib().scn_input_rules_workspace(n))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().scn_input_layer_rules(L.ptr(keys_in), n, L.ptr(tk), L.ptr(tv), cap, L.ptr(rows), L.ptr(keys_out),
+                                          L.ptr(n_active), L.ptr(ws), ws_bytes, L.stream()), "scn_input_layer_rules")
+    na = int(n_active.item())
+    return rows, keys_out[:na], tk, tv, cap
+
+
+def subm_rulebook(keys, tk, tv, cap, filt) -> torch.Tensor:
+    n = keys.shape[0]
+    n_pad = pad128(n)
+    K = filt[0] * filt[1] * filt[2]
+    nbr = torch.empty((K, n_pad), dtype=torch.int32, device=keys.device)
+    L.check(L.lib().scn_subm_rulebook(L.ptr(keys), n, L.ptr(tk), L.ptr(tv), cap, filt[0], filt[1], filt[2],
+                                      L.ptr(nbr), n_pad, L.stream()), "scn_subm_rulebook")
+    return nbr
+
+
+def strided_rulebook(keys_in, stride):
+    """-> (keys_out int64 [n_out] sorted, out_row_of_in int32 [n], off_of_in int32 [n]).  One D2H sync."""
+    n = keys_in.shape[0]
+    dev = keys_in.device
+    keys_out = torch.empty((n,), dtype=torch.int64, device=dev)
+    out_row = _i32(n, dev)
+    off = _i32(n, dev)
+    n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
+    ws_bytes = int(L.lib().scn_strided_workspace(n))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().scn_strided_rulebook(L.ptr(keys_in), n, stride[0], stride[1], stride[2], L.ptr(keys_out),
+                                         L.ptr(out_row), L.ptr(off), L.ptr(n_out), L.ptr(ws), ws_bytes, L.stream()),
+            "scn_strided_rulebook")
+    m = int(n_out.item())
+    return keys_out[:m], out_row, off
+
+
+def strided_tables(out_row, off, K, n_in, n_out):
+    dev = out_row.device
+    down = torch.empty((K, pad128(n_out)), dtype=torch.int32, device=dev)
+    up = torch.empty((K, pad128(n_in)), dtype=torch.int32, device=dev)
+    L.check(L.lib().scn_strided_tables(L.ptr(out_row), L.ptr(off), n_in, K, L.ptr(down), pad128(n_out), L.ptr(up),
+                                       pad128(n_in), L.stream()), "scn_strided_tables")
+    return down, up
+
+
+def rulebook_pairs(nbr: torch.Tensor, n: int):
+    """SCN-format rulebook: list of K int32 [P_k, 2] (in,out) tensors, pairs sorted by out row."""
+    K, n_pad = nbr.shape
+    dev = nbr.device
+    counts = torch.zeros((K,), dtype=torch.int32, device=dev)
+    L.check(L.lib().scn_rulebook_count(L.ptr(nbr), K, n, n_pad, L.ptr(counts), L.stream()), "scn_rulebook_count")
+    total = int(counts.sum().item())
+    pin, pout = _i32(max(total, 1), dev), _i32(max(total, 1), dev)
+    offs = _i32(K + 1, dev)
+    ws_bytes = int(L.lib().scn_rulebook_workspace(K, n_pad))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    L.check(L.lib().scn_rulebook_pairs(L.ptr(nbr), K, n, n_pad, L.ptr(pin), L.ptr(pout), L.ptr(offs), L.ptr(ws),
+                                       ws_bytes, L.stream()), "scn_rulebook_pairs")
+    o = offs.cpu().tolist()
+    return [torch.stack([pin[o[k]:o[k + 1]], pout[o[k]:o[k + 1]]], 1) for k in range(K)]
+
+
+# ---------------------------------------------------------------------------- convolution
+
+
+def conv_uses_tc(K, n_in, n_out, prec) -> bool:
+    return bool(L.lib().scn_conv_uses_tensor_cores(K, n_in, n_out, prec))
+
+
+def prep_weights(w3: torch.Tensor, transpose: bool, mirror: bool, prec: int) -> torch.Tensor:
+    """w3: fp32 [K, Cin, Cout] -> B_k laid out for the kernel that will run (bf16 Bt or fp32 B)."""
+    K, cin, cout = w3.shape
+    n_in, n_out = (cout, cin) if transpose else (cin, cout)
+    tc = conv_uses_tc(K, n_in, n_out, prec)
+    out = torch.empty((K * cin * cout,), dtype=torch.bfloat16 if tc else torch.float32, device=w3.device)
+    L.check(L.lib().scn_conv_prep_weights(L.ptr(w3), K, cin, cout, int(transpose), int(mirror), prec, L.ptr(out),
+                                          L.stream()), "scn_conv_prep_weights")
+    return out
+
+
+def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype) -> torch.Tensor:
+    K, n_pad = nbr.shape
+    if conv_uses_tc(K, n_in, n_out, prec) and x.dtype != out_dtype:
+        x = convert(x, out_dtype)
+    out = torch.empty((n_out_rows, n_out), dtype=out_dtype, device=x.device)
+    L.check(L.lib().scn_conv_forward(L.ptr(x), L.dtype_code(x), x.shape[0], L.ptr(nbr), K, n_out_rows, n_pad, n_in,
+                                     n_out, L.ptr(bprep), L.ptr(bias), prec, L.ptr(out), L.dtype_code(out),
+                                     L.stream()), "scn_conv_forward")
+    return out
+
+
+def conv_wgrad(x, dout, nbr, n_rows, n_in, n_out, prec) -> torch.Tensor:
+    K, n_pad = nbr.shape
+    if conv_uses_tc(K, n_in, n_out, prec) and x.dtype != dout.dtype:
+        x = convert(x, dout.dtype)
+    dw = torch.zeros((K, n_in, n_out), dtype=torch.float32, device=x.device)
+    L.check(L.lib().scn_conv_wgrad(L.ptr(x), L.dtype_code(x), L.ptr(dout), L.dtype_code(dout), L.ptr(nbr), K, n_rows,
+                                   n_pad, n_in, n_out, prec, L.ptr(dw), L.stream()), "scn_conv_wgrad")
+    return dw
+
+
+def col_sum(x) -> torch.Tensor:
+    n, c = x.shape
+    ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
+    out = torch.empty((c,), dtype=torch.float32, device=x.device)
+    L.check(L.lib().scn_col_sum(L.ptr(x), L.dtype_code(x), n, c, L.ptr(ws), L.ptr(out), L.stream()), "scn_col_sum")
+    return out
+
+
+# ---------------------------------------------------------------------------- bandwidth layers
+
+
+def bn_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak):
+    n, c = x.shape
+    dev = x.device
+    save_mean = torch.empty((c,), dtype=torch.float32, device=dev)
+    save_invstd = torch.empty((c,), dtype=torch.float32, device=dev)
+    ws = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    out = torch.empty_like(x)
+    L.check(L.lib().scn_bn_forward(L.ptr(x), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta), L.ptr(rm), L.ptr(rv),
+                                   int(training), eps, momentum, leak, L.ptr(save_mean), L.ptr(save_invstd),
+                                   L.ptr(ws), L.ptr(out), L.stream()), "scn_bn_forward")
+    return out, save_mean, save_invstd
+
+
+def bn_backward(x, dout, gamma, beta, save_mean, save_invstd, training, leak):
+    n, c = x.shape
+    dev = x.device
+    ws = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    dx = torch.empty_like(x)
+    dgamma = torch.empty((c,), dtype=torch.float32, device=dev)
+    dbeta = torch.empty((c,), dtype=torch.float32, device=dev)
+    L.check(L.lib().scn_bn_backward(L.ptr(x), L.ptr(dout), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta),
+                                    L.ptr(save_mean), L.ptr(save_invstd), int(training), leak, L.ptr(ws), L.ptr(dx),
+                                    L.ptr(dgamma), L.ptr(dbeta), L.stream()), "scn_bn_backward")
+    return dx, dgamma, dbeta
+
+
+def leaky_forward(x, leak):
+    out = torch.empty_like(x)
+    L.check(L.lib().scn_leaky_forward(L.ptr(x), L.dtype_code(x), x.numel(), leak, L.ptr(out), L.stream()),
+            "scn_leaky_forward")
+    return out
+
+
+def leaky_backward(x, dout, leak):
+    dx = torch.empty_like(x)
+    L.check(L.lib().scn_leaky_backward(L.ptr(x), L.ptr(dout), L.dtype_code(x), x.numel(), leak, L.ptr(dx),
+                                       L.stream()), "scn_leaky_backward")
+    return dx
+
+
+def add_forward(a, b, leak=1.0):
+    out = torch.empty_like(a)
+    L.check(L.lib().scn_add_forward(L.ptr(a), L.ptr(b), L.dtype_code(a), a.numel(), leak, L.ptr(out), L.stream()),
+            "scn_add_forward")
+    return out
+
+
+def convert(x, dtype):
+    if x.dtype == dtype:
+        return x
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    if x.numel():
+        L.check(L.lib().scn_rows_gather(L.ptr(x), L.dtype_code(x), None, x.numel(), 1, L.ptr(out), L.dtype_code(out),
+                                        L.stream()), "scn_rows_gather(convert)")
+    return out
+
+
+def input_layer_forward(feats, rows, n_active, mode):
+    n_in, c = feats.shape
+    dev = feats.device
+    out = torch.empty((n_active, c), dtype=torch.float32, device=dev)
+    cnt = torch.empty((n_active,), dtype=torch.float32, device=dev) if mode == 4 else None
+    L.check(L.lib().scn_input_layer_forward(L.ptr(feats), L.ptr(rows), n_in, n_active, c, mode, L.ptr(out), L.SCN_F32,
+                                            L.ptr(cnt), L.stream()), "scn_input_layer_forward")
+    return out
+
+
+def rows_gather(src, rows, out_dtype):
+    n = rows.shape[0]
+    c = src.shape[1]
+    out = torch.empty((n, c), dtype=out_dtype, device=src.device)
+    L.check(L.lib().scn_rows_gather(L.ptr(src), L.dtype_code(src), L.ptr(rows), n, c, L.ptr(out), L.dtype_code(out),
+                                    L.stream()), "scn_rows_gather")
+    return out
+
+
+def rows_scatter_add(src, rows, n_out):
+    c = src.shape[1]
+    out = torch.zeros((n_out, c), dtype=torch.float32, device=src.device)
+    L.check(L.lib().scn_rows_scatter_add(L.ptr(src), L.dtype_code(src), L.ptr(rows), rows.shape[0], c, L.ptr(out),
+                                         L.stream()), "scn_rows_scatter_add")
+    return out
+
+
+def sparse_to_dense_forward(x, keys, batch, spatial):
+    n, c = x.shape
+    dense = torch.empty((batch, c) + tuple(spatial), dtype=torch.float32, device=x.device)
+    L.check(L.lib().scn_sparse_to_dense_forward(L.ptr(x), L.dtype_code(x), L.ptr(keys), n, c, batch, spatial[0],
+                                                spatial[1], spatial[2], L.ptr(dense), L.stream()),
+            "scn_sparse_to_dense_forward")
+    return dense
+
+
+def sparse_to_dense_backward(ddense, keys, n, c, batch, spatial, dtype):
+    dx = torch.empty((n, c), dtype=dtype, device=ddense.device)
+    L.check(L.lib().scn_sparse_to_dense_backward(L.ptr(ddense), L.ptr(keys), n, c, batch, spatial[0], spatial[1],
+                                                 spatial[2], L.ptr(dx), L.dtype_code(dx), L.stream()),
+            "scn_sparse_to_dense_backward")
+    return dx
