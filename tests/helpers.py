@@ -37,12 +37,44 @@ def blob_sites(n, grid, batch, seed):
 
 
 def rel_err(a, b):
-    a = torch.as_tensor(a).double()
-    b = torch.as_tensor(b).double()
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
 def rel_l2(a, b):
-    a = torch.as_tensor(a).double()
-    b = torch.as_tensor(b).double()
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def init_deterministic(model, seed=7):
+    """Fills every parameter/buffer from numpy PCG64 keyed by its name: identical on any box, any torch
+    (used by tests/golden/make_golden.py and by the tests that replay the fixtures)."""
+    import zlib
+    with torch.no_grad():
+        for name, p in list(model.named_parameters()) + list(model.named_buffers()):
+            rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
+            if name.endswith("running_var"):
+                v = rng.uniform(0.5, 1.5, size=tuple(p.shape))
+            elif name.endswith("running_mean"):
+                v = rng.normal(0, 0.1, size=tuple(p.shape))
+            elif p.dim() >= 3:                         # conv weight [K,1,Cin,Cout]
+                fan = p.shape[0] * p.shape[-2]
+                v = rng.normal(0, np.sqrt(2.0 / fan), size=tuple(p.shape))
+            elif p.dim() == 2:                         # Linear
+                v = rng.normal(0, np.sqrt(1.0 / p.shape[1]), size=tuple(p.shape))
+            elif name.endswith("norm.weight"):
+                v = rng.uniform(0.8, 1.2, size=tuple(p.shape))
+            else:
+                v = rng.normal(0, 0.05, size=tuple(p.shape))
+            p.copy_(torch.as_tensor(v, dtype=p.dtype))
+
+
+def small_batch(dataset, batch=2, seed=4321, max_voxels=6000):
+    """The seeded synthetic mini-batch the golden fixtures were generated on."""
+    from sparseeventid_b200 import synthetic
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
+    if dataset == "dune3d":
+        return larcvsparse_to_scnsparse_3d(synthetic.larcv_batch_3d(batch, seed=seed, max_voxels=max_voxels))
+    return larcvsparse_to_scnsparse_2d(synthetic.larcv_batch_2d(batch, seed=seed, max_voxels=max_voxels))

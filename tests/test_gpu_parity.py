@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_FP32 = 1e-4
 TOL_BF16 = 2e-3
+ABS_FLOOR = 1e-3
 
 
 @pytest.fixture(scope="module")
@@ -53,11 +54,13 @@ def check(a, b, mode, what):
     assert a.shape == b.shape, what
     if b.numel() == 0:
         return
+    # Quantities whose exact value is 0 (e.g. the gradient of a conv bias that feeds a BatchNorm) carry
+    # only rounding noise on both sides: the denominator is floored at ABS_FLOOR per element.
     if mode == "fp32":
-        e = rel_err(a, b)
+        e = float((a - b).abs().max() / b.abs().max().clamp_min(ABS_FLOOR))
         assert e <= TOL_FP32, f"{what}: rel max err {e:.3e} > {TOL_FP32}"
     else:
-        e = rel_l2(a, b)
+        e = float((a - b).double().norm() / b.double().norm().clamp_min(ABS_FLOOR * b.numel() ** 0.5))
         assert e <= TOL_BF16, f"{what}: rel L2 err {e:.3e} > {TOL_BF16}"
 
 
