@@ -53,6 +53,8 @@ extern "C" {
 
 /* Library version / build info: "scn_b200 <ver> sm_100a". */
 const char* scn_version(void);
+/* Number of kernels of this library launched by this process so far (bench.py's gpu_launches). */
+uint64_t scn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Coordinate hash (replaces google::dense_hash_map<Point<D>,Int> inside SCN's Metadata).

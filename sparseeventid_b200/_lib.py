@@ -23,6 +23,7 @@ _p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 # name -> (restype, argtypes); mirrors include/scn_b200.h one to one
 SIGNATURES = {
     "scn_version": (C.c_char_p, []),
+    "scn_launch_count": (C.c_uint64, []),
     "scn_hash_capacity": (_i64, [_i64]),
     "scn_pack_coords": (_i, [_p, _i, _i64, _i, _i, _p, _p]),
     "scn_unpack_keys": (_i, [_p, _i64, _p, _p]),

@@ -6,8 +6,11 @@
 
 #include "../../include/scn_b200.h"
 
+// number of kernels of THIS library launched so far (library kernels such as CUB's are not counted)
+extern unsigned long long g_scn_launch_count;
 #define SCN_LAUNCH_CHECK()                                \
   do {                                                    \
+    ++g_scn_launch_count;                                 \
     cudaError_t e__ = cudaGetLastError();                 \
     if (e__ != cudaSuccess) return (int)e__;              \
   } while (0)

@@ -117,7 +117,10 @@ size_t scan_temp_bytes(int64_t n) {
 
 }  // namespace
 
+unsigned long long g_scn_launch_count = 0;
+
 extern "C" const char* scn_version(void) { return "scn_b200 0.1 sm_100a"; }
+extern "C" uint64_t scn_launch_count(void) { return (uint64_t)g_scn_launch_count; }
 
 extern "C" int64_t scn_hash_capacity(int64_t n) {
   int64_t c = 1024;

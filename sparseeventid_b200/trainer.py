@@ -1,0 +1,118 @@
+"""Event-sharded data-parallel training step for the sparse ResNet.
+
+Replaces, for this path only, the reference's Lightning DDPStrategy / Horovod DistributedOptimizer
+(src/utils/create_trainer.py:46-60, src/utils/torch/distributed_trainer.py:95): one process per GPU,
+events are independent so the batch is split by event, BatchNorm statistics stay per rank (no SyncBN in
+the reference), and the only exchange is the gradient mean -- done here on ONE flat fp32 gradient arena,
+all-reduced bucket by bucket from autograd hooks so NCCL (NVLink 5 / NVSwitch) overlaps the rest of
+the backward.  Loss / optimizer follow src/utils/supervised_eventID.py:168-207 and
+src/utils/training_utils.py:13 (Adam lr=1.0 x schedule, eps 1e-6, betas (0.8, 0.9), weight decay 1e-6).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import networks
+
+
+class FlatGradArena:
+    """All parameter gradients as views into one fp32 buffer; bucketed async all-reduce from hooks."""
+
+    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 32 << 20, process_group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # parameters are laid out in REVERSE registration order: the backward produces gradients roughly
+        # from the last layer to the first, so bucket 0 fills first and its all-reduce starts earliest
+        self.buckets = []            # (start, end, n_params)
+        self._bucket_of: Dict[int, int] = {}
+        off = 0
+        b_start, b_count = 0, 0
+        for p in reversed(self.params):
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[id(p)] = len(self.buckets)
+            off += n
+            b_count += 1
+            if (off - b_start) * 4 >= bucket_bytes:
+                self.buckets.append((b_start, off, b_count))
+                b_start, b_count = off, 0
+        if b_count:
+            self.buckets.append((b_start, off, b_count))
+        self._pending = [0] * len(self.buckets)
+        self._works = []
+        self._hooks = []
+        if self.world > 1:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def zero(self):
+        self.flat.zero_()
+        self._pending = [c for (_, _, c) in self.buckets]
+        self._works = []
+
+    def _on_grad(self, p):
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            s, e, _ = self.buckets[b]
+            self._works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self):
+        """Waits for the in-flight bucket all-reduces and turns the sums into means."""
+        if self.world == 1:
+            return
+        for b, left in enumerate(self._pending):      # parameters that received no gradient this step
+            if left > 0:
+                s, e, _ = self.buckets[b]
+                self._works.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, group=self.group,
+                                                   async_op=True))
+                self._pending[b] = 0
+        for w in self._works:
+            w.wait()
+        self._works = []
+        self.flat.mul_(1.0 / self.world)
+
+
+def warmup_flat_lr(step: int, peak: float = 3e-3, warmup_steps: int = 100) -> float:
+    """First two segments of WarmupFlatDecay (src/utils/learning_rate_scheduler.py:92-126)."""
+    if step < warmup_steps:
+        return 1e-5 + (peak - 1e-5) * step / max(warmup_steps, 1)
+    return peak
+
+
+class Trainer:
+    def __init__(self, scn, dataset: str = "dune3d", device="cuda", cfg: Optional[networks.EncoderConfig] = None,
+                 seed: int = 0, weight_decay: float = 1e-6, peak_lr: float = 3e-3, fused_adam: Optional[bool] = None):
+        torch.manual_seed(seed)
+        enc, head = networks.build_networks(scn, dataset, cfg)
+        self.model = networks.EventIDModel(enc, head).to(device)
+        self.device = torch.device(device)
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:      # rank 0's initial weights everywhere (distributed_trainer.py:127-133)
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                dist.broadcast(t.data, src=0)
+        self.arena = FlatGradArena(list(self.model.parameters()))
+        if fused_adam is None:
+            fused_adam = self.device.type == "cuda"
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=1.0, eps=1e-6, betas=(0.8, 0.9),
+                                    weight_decay=weight_decay, fused=fused_adam)
+        self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: warmup_flat_lr(s, peak_lr))
+        self.model.train()
+
+    def step(self, batch, labels):
+        """batch: (coords [N,4], features [N,1], batch_size) on self.device; labels: dict of int64 [B]."""
+        self.arena.zero()
+        logits = self.model(batch)
+        loss = networks.focal_loss(labels, logits)
+        loss.backward()
+        self.arena.finish()
+        self.opt.step()
+        self.sched.step()
+        return loss

@@ -197,8 +197,15 @@ def run_pair(scn, mode, make_gpu, make_ref, coords, grid, batch, cin, seed=0, de
         yr.backward(dout.double())
         yg.backward(dout.cuda().to(yg.dtype))
         check(f_gpu.grad, f_ref.grad, mode, "grad input")
+        ref_norms = [float(p.grad.norm()) for r in ref_mods for p in r.parameters()]
+        scale = max(ref_norms) if ref_norms else 1.0
         for g, r in zip(gpu_mods, ref_mods):
             for (n1, p1), (n2, p2) in zip(g.named_parameters(), r.named_parameters()):
+                if float(p2.grad.norm()) < 1e-3 * scale:
+                    # structurally zero gradient (a conv bias feeding a BatchNorm): only rounding noise on
+                    # either side, so it is required to be small rather than relatively equal
+                    assert float(p1.grad.float().norm()) < 1e-2 * scale, f"grad {n1} should be ~0"
+                    continue
                 check(p1.grad, p2.grad, mode, f"grad {n1}")
             for (n1, b1), (n2, b2) in zip(g.named_buffers(), r.named_buffers()):
                 assert rel_err(b1, b2) < 1e-4, f"buffer {n1}"
