@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- 3D sparse ResNet (recipes/dune3d.yaml encoder + heads) TRAINING events/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" = one full training step of the hot path over one batch of synthetic DUNE-shaped events:
+InputLayer (hash + row numbering) -> rulebooks -> 56 sparse convolutions + 53 BatchNorms ... ->
+SparseToDense -> heads -> focal loss -> backward -> gradient all-reduce (N>1) -> Adam.
+Workload at N=1 = BASELINE.json configs[2] per GPU ("3D sparse ResNet training, event-sharded data
+parallel, batch 64/GPU, bf16 tensor-core convs"); weak scaling (64 events on every rank).
+
+Prints ONE JSON line (rank 0).  `value` = events/s with the batch already resident in HBM;
+`e2e` = events/s through the public module API starting from pinned HOST buffers (H2D of the SCN input
+tuple + labels, D2H of the loss, every step).  `roofline` describes the dominant kernel family (the
+gather-GEMM convolution kernels), timed live with CUDA events on the launching stream in a separate
+instrumented pass after the timed region.  `cpu_baseline` = the oracle port of SparseConvNet's CPU
+algorithm on the host cores, on a bounded sample.  `--impl reference` times that CPU arm alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+METRIC = "3D sparse ResNet train events/sec"
+UNIT = "events/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ------------------------------------------------------------------------------------------- data
+
+
+def host_batch(batch, seed, dataset):
+    """Synthetic larcv batch -> SCN input tuple exactly as the reference's transform produces it
+    (coords float64 [N,4] with the batch index last, features float32 [N,1]) + 4 label vectors."""
+    from sparseeventid_b200 import synthetic
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
+    if dataset == "dune3d":
+        coords, feats, bs = larcvsparse_to_scnsparse_3d(synthetic.larcv_batch_3d(batch, seed=seed))
+    else:
+        coords, feats, bs = larcvsparse_to_scnsparse_2d(synthetic.larcv_batch_2d(batch, seed=seed))
+    labels = synthetic.make_labels(batch, seed=seed)
+    return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+
+
+def cpu_events_per_s(dataset, events, steps, warmup, seed=1234):
+    """Oracle port of SparseConvNet's CPU path (per-offset index_select -> mm -> index_add_) running the
+    same encoder + heads + focal loss + Adam, all host threads.  Returns (events/s, seconds/step, cores)."""
+    from oracle import sparseconvnet_oracle as oscn
+    from sparseeventid_b200 import networks
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    oscn.set_numerics("fp32")
+    enc, head = networks.build_networks(oscn, dataset)
+    model = networks.EventIDModel(enc, head)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1.0 * 3e-3, eps=1e-6, betas=(0.8, 0.9), weight_decay=1e-6)
+    times = []
+    for it in range(warmup + steps):
+        coords, feats, bs, labels = host_batch(events, seed + 1000 * it, dataset)
+        lab = {k: torch.as_tensor(v) for k, v in labels.items()}
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        loss = networks.focal_loss(lab, model((torch.as_tensor(coords), torch.as_tensor(feats), bs)))
+        loss.backward()
+        opt.step()
+        float(loss.detach())
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return events / sec, sec, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    events = args.cpu_events
+    v, sec, cores = cpu_events_per_s(args.dataset, events, args.steps, min(args.warmup, 1))
+    sample = (f"{events} synthetic {args.dataset} events per step (bounded sample of the batch-{args.batch} workload), "
+              f"{args.steps} timed steps after {min(args.warmup, 1)} warm-up, fp32")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.dataset} default encoder+heads training step, CPU, {events} events/step",
+                   "note": "SparseConvNet itself is absent from the image; this is the oracle port of its CPU "
+                           "algorithm (kind=port)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+
+
+def conv_algorithmic(rec, elem_bytes):
+    """FLOPs / compulsory bytes of one conv launch."""
+    P, K, n_in, n_out = rec["pairs"], rec["K"], rec["n_in"], rec["n_out"]
+    flops = 2.0 * P * n_in * n_out
+    rows_in, rows_out = rec["rows_in"], rec["rows_out"]
+    if rec["kind"] == "conv_wgrad":
+        by = rows_in * n_in * elem_bytes + rows_out * n_out * elem_bytes + K * n_in * n_out * 4 + 8 * P
+    else:
+        by = rows_in * n_in * elem_bytes + rows_out * n_out * elem_bytes + K * n_in * n_out * 2 + 8 * P
+    return flops, by
+
+
+def run_ours(args, rank, world, local_rank):
+    import sparseconvnet as scn
+    from sparseeventid_b200 import _lib
+    from sparseeventid_b200.scn import ops
+    from sparseeventid_b200.trainer import Trainer
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    scn.set_precision(args.precision)
+    peaks = load_peaks()
+    trainer = Trainer(scn, args.dataset, device=dev, seed=0)
+    lib = _lib.lib()
+
+    # ---- inputs: a pool of distinct host batches per rank (pinned), mirrored on the device
+    pool = []
+    for i in range(args.pool):
+        coords, feats, bs, labels = host_batch(args.batch, 1234 + 100000 * rank + 1000 * i, args.dataset)
+        h = {"coords": torch.from_numpy(coords).pin_memory(), "feats": torch.from_numpy(feats).pin_memory(),
+             "labels": {k: torch.from_numpy(v).pin_memory() for k, v in labels.items()}, "bs": bs}
+        pool.append(h)
+    dpool = [{"coords": h["coords"].to(dev), "feats": h["feats"].to(dev),
+              "labels": {k: v.to(dev) for k, v in h["labels"].items()}, "bs": h["bs"]} for h in pool]
+    n_voxels = int(np.mean([h["coords"].shape[0] for h in pool]))
+    h2d_bytes = int(np.mean([h["coords"].numel() * 8 + h["feats"].numel() * 4 + 4 * 8 * args.batch for h in pool]))
+
+    def step_resident(i):
+        d = dpool[i % len(dpool)]
+        return trainer.step((d["coords"], d["feats"], d["bs"]), d["labels"])
+
+    def step_e2e(i):
+        h = pool[i % len(pool)]
+        c = h["coords"].to(dev, non_blocking=True)
+        f = h["feats"].to(dev, non_blocking=True)
+        lab = {k: v.to(dev, non_blocking=True) for k, v in h["labels"].items()}
+        loss = trainer.step((c, f, h["bs"]), lab)
+        return float(loss.detach().cpu())          # D2H of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.scn_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lib.scn_launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, int(launches)
+
+    for i in range(args.warmup):
+        step_resident(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    value = args.batch * world * args.steps / (ms * 1e-3)
+    e2e = args.batch * world * args.steps / (ms_e2e * 1e-3)
+
+    # ---- instrumented pass (rank 0): CUDA events around every launch of this library's hot kernels
+    roof, breakdown = None, None
+    if rank == 0:
+        prof = ops.Profiler()
+        ops.set_profiler(prof)
+        for i in range(2):
+            step_resident(i)
+        ops.set_profiler(None)
+        torch.cuda.synchronize()
+        recs = prof.finish()
+        eb = 2 if args.precision == "bf16" else 4
+        agg = {}
+        for r in recs:
+            a = agg.setdefault(r["kind"], {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            a["ms"] += r["ms"]; a["launches"] += 1
+            if r["kind"].startswith("conv"):
+                fl, by = conv_algorithmic(r, eb)
+                a["flops"] += fl; a["bytes"] += by
+            else:
+                a["bytes"] += r.get("bytes", 0.0)
+        tc = [r for r in recs if r["kind"] in ("conv_fwd", "conv_dgrad") and r["tc"]]
+        if tc:
+            fl = sum(conv_algorithmic(r, eb)[0] for r in tc)
+            by = sum(conv_algorithmic(r, eb)[1] for r in tc)
+            t = sum(r["ms"] for r in tc) * 1e-3
+            peak = peaks["bf16_tflops_sustained"]
+            roof = {"bound": "tensor", "kernel": "gather-GEMM conv fwd/dgrad (k_conv_*)", "achieved": fl / t / 1e12,
+                    "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": None,
+                    "launches": len(tc), "avg_launch_us": t / len(tc) * 1e6,
+                    "flops_per_launch": fl / len(tc), "algorithmic_bytes_per_launch": by / len(tc),
+                    "achieved_algorithmic_gbs": by / t / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+                    "frac_of_hbm": by / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["_source"],
+                    "share_of_step": sum(r["ms"] for r in tc) / 2 / (ms / args.steps)}
+        breakdown = {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] / 2,
+                         "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None,
+                         "algorithmic_gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None}
+                     for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"bench_breakdown_n{world}.json"), "w") as f:
+            json.dump({"ms_per_step": ms / args.steps, "breakdown": breakdown,
+                       "per_launch": [{k: v for k, v in r.items()} for r in recs[: len(recs) // 2]]}, f, indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores = cpu_events_per_s(args.dataset, args.cpu_events, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{args.cpu_events} events/step x 2 timed steps (+1 warm-up) of the same encoder+heads "
+                         f"training step through the oracle port of SparseConvNet's CPU algorithm, fp32"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.dataset} default encoder (56 sparse convs, 20.9M params) + 4 heads, training "
+                                   f"step, batch {args.batch} events/GPU, precision mode {args.precision}",
+                       "events_per_gpu": args.batch, "mean_voxels_per_batch": n_voxels, "parallelism": f"dp{world}",
+                       "l2_policy": "inputs_larger_than_L2 (activations of one step >> 126 MB; "
+                                    f"{args.pool} distinct batches cycled)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "breakdown_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in (breakdown or {}).items()},
+        }
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dataset", default="dune3d", choices=["dune3d", "dune2d"])
+    ap.add_argument("--batch", type=int, default=64, help="events per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "mixed", "fp32"])
+    ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled per rank")
+    ap.add_argument("--cpu-events", type=int, default=8, help="events per step of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -45,7 +45,8 @@ class ConvFn(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec)
-            dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype)
+            dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
+                                  kind="conv_dgrad")
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(x, dout, ctx.nbr_fwd, ctx.n_out_rows, cin, cout, ctx.prec).view_as(weight)
             dw = dw.to(weight.dtype)

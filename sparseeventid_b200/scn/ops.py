@@ -10,6 +10,48 @@ import torch
 from .. import _lib as L
 
 
+class Profiler:
+    """CUDA-event timing of individual C-ABI calls on the launching stream (bench.py's roofline pass)."""
+
+    def __init__(self):
+        self.recs = []
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, e0, **meta):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        meta["_e0"], meta["_e1"] = e0, e1
+        self.recs.append(meta)
+
+    def finish(self):
+        torch.cuda.synchronize()
+        pairs = {}
+        out = []
+        for r in self.recs:
+            r = dict(r)
+            r["ms"] = r.pop("_e0").elapsed_time(r.pop("_e1"))
+            nbr = r.pop("nbr", None)
+            if nbr is not None:
+                key = (nbr.data_ptr(), tuple(nbr.shape))
+                if key not in pairs:
+                    pairs[key] = int((nbr >= 0).sum().item())
+                r["pairs"] = pairs[key]
+            out.append(r)
+        return out
+
+
+_profiler = None
+
+
+def set_profiler(p):
+    global _profiler
+    _profiler = p
+
+
 def _i32(n, device):
     return torch.empty((n,), dtype=torch.int32, device=device)
 
@@ -72,8 +114,12 @@ def input_layer_rules(keys_in: torch.Tensor):
     n_active = torch.zeros((1,), dtype=torch.int32, device=dev)
     ws_bytes = int(L.lib().scn_input_rules_workspace(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_input_layer_rules(L.ptr(keys_in), n, L.ptr(tk), L.ptr(tv), cap, L.ptr(rows), L.ptr(keys_out),
                                           L.ptr(n_active), L.ptr(ws), ws_bytes, L.stream()), "scn_input_layer_rules")
+    if p:
+        p.end(e0, kind="rulebook_input", bytes=20.0 * n, rows=n)
     na = int(n_active.item())
     return rows, keys_out[:na], tk, tv, cap
 
@@ -83,8 +129,12 @@ def subm_rulebook(keys, tk, tv, cap, filt) -> torch.Tensor:
     n_pad = pad128(n)
     K = filt[0] * filt[1] * filt[2]
     nbr = torch.empty((K, n_pad), dtype=torch.int32, device=keys.device)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_subm_rulebook(L.ptr(keys), n, L.ptr(tk), L.ptr(tv), cap, filt[0], filt[1], filt[2],
                                       L.ptr(nbr), n_pad, L.stream()), "scn_subm_rulebook")
+    if p:
+        p.end(e0, kind="rulebook_subm", bytes=8.0 * n + 4.0 * K * n_pad, K=K, rows=n)
     return nbr
 
 
@@ -98,9 +148,13 @@ def strided_rulebook(keys_in, stride):
     n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
     ws_bytes = int(L.lib().scn_strided_workspace(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_strided_rulebook(L.ptr(keys_in), n, stride[0], stride[1], stride[2], L.ptr(keys_out),
                                          L.ptr(out_row), L.ptr(off), L.ptr(n_out), L.ptr(ws), ws_bytes, L.stream()),
             "scn_strided_rulebook")
+    if p:
+        p.end(e0, kind="rulebook_strided", bytes=24.0 * n, rows=n)
     m = int(n_out.item())
     return keys_out[:m], out_row, off
 
@@ -149,14 +203,19 @@ def prep_weights(w3: torch.Tensor, transpose: bool, mirror: bool, prec: int) -> 
     return out
 
 
-def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype) -> torch.Tensor:
+def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, kind="conv_fwd") -> torch.Tensor:
     K, n_pad = nbr.shape
-    if conv_uses_tc(K, n_in, n_out, prec) and x.dtype != out_dtype:
+    tc = conv_uses_tc(K, n_in, n_out, prec)
+    if tc and x.dtype != out_dtype:
         x = convert(x, out_dtype)
     out = torch.empty((n_out_rows, n_out), dtype=out_dtype, device=x.device)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_conv_forward(L.ptr(x), L.dtype_code(x), x.shape[0], L.ptr(nbr), K, n_out_rows, n_pad, n_in,
                                      n_out, L.ptr(bprep), L.ptr(bias), prec, L.ptr(out), L.dtype_code(out),
                                      L.stream()), "scn_conv_forward")
+    if p:
+        p.end(e0, kind=kind, K=K, n_in=n_in, n_out=n_out, rows_in=x.shape[0], rows_out=n_out_rows, nbr=nbr, tc=tc)
     return out
 
 
@@ -165,8 +224,13 @@ def conv_wgrad(x, dout, nbr, n_rows, n_in, n_out, prec) -> torch.Tensor:
     if conv_uses_tc(K, n_in, n_out, prec) and x.dtype != dout.dtype:
         x = convert(x, dout.dtype)
     dw = torch.zeros((K, n_in, n_out), dtype=torch.float32, device=x.device)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_conv_wgrad(L.ptr(x), L.dtype_code(x), L.ptr(dout), L.dtype_code(dout), L.ptr(nbr), K, n_rows,
                                    n_pad, n_in, n_out, prec, L.ptr(dw), L.stream()), "scn_conv_wgrad")
+    if p:
+        p.end(e0, kind="conv_wgrad", K=K, n_in=n_in, n_out=n_out, rows_in=x.shape[0], rows_out=n_rows, nbr=nbr,
+              tc=conv_uses_tc(K, n_in, n_out, prec))
     return dw
 
 
@@ -188,9 +252,13 @@ def bn_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak):
     save_invstd = torch.empty((c,), dtype=torch.float32, device=dev)
     ws = torch.empty((2 * c,), dtype=torch.float64, device=dev)
     out = torch.empty_like(x)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_bn_forward(L.ptr(x), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta), L.ptr(rm), L.ptr(rv),
                                    int(training), eps, momentum, leak, L.ptr(save_mean), L.ptr(save_invstd),
                                    L.ptr(ws), L.ptr(out), L.stream()), "scn_bn_forward")
+    if p:   # stats pass reads x, apply pass reads x and writes out
+        p.end(e0, kind="bn_fwd", bytes=3.0 * x.numel() * x.element_size())
     return out, save_mean, save_invstd
 
 
@@ -201,30 +269,46 @@ def bn_backward(x, dout, gamma, beta, save_mean, save_invstd, training, leak):
     dx = torch.empty_like(x)
     dgamma = torch.empty((c,), dtype=torch.float32, device=dev)
     dbeta = torch.empty((c,), dtype=torch.float32, device=dev)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_bn_backward(L.ptr(x), L.ptr(dout), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta),
                                     L.ptr(save_mean), L.ptr(save_invstd), int(training), leak, L.ptr(ws), L.ptr(dx),
                                     L.ptr(dgamma), L.ptr(dbeta), L.stream()), "scn_bn_backward")
+    if p:   # reduce pass reads x,dout; apply pass reads x,dout and writes dx
+        p.end(e0, kind="bn_bwd", bytes=5.0 * x.numel() * x.element_size())
     return dx, dgamma, dbeta
 
 
 def leaky_forward(x, leak):
     out = torch.empty_like(x)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_leaky_forward(L.ptr(x), L.dtype_code(x), x.numel(), leak, L.ptr(out), L.stream()),
             "scn_leaky_forward")
+    if p:
+        p.end(e0, kind="leaky_fwd", bytes=2.0 * x.numel() * x.element_size())
     return out
 
 
 def leaky_backward(x, dout, leak):
     dx = torch.empty_like(x)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_leaky_backward(L.ptr(x), L.ptr(dout), L.dtype_code(x), x.numel(), leak, L.ptr(dx),
                                        L.stream()), "scn_leaky_backward")
+    if p:
+        p.end(e0, kind="leaky_bwd", bytes=3.0 * x.numel() * x.element_size())
     return dx
 
 
 def add_forward(a, b, leak=1.0):
     out = torch.empty_like(a)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_add_forward(L.ptr(a), L.ptr(b), L.dtype_code(a), a.numel(), leak, L.ptr(out), L.stream()),
             "scn_add_forward")
+    if p:
+        p.end(e0, kind="add", bytes=3.0 * a.numel() * a.element_size())
     return out
 
 
@@ -268,9 +352,13 @@ def rows_scatter_add(src, rows, n_out):
 def sparse_to_dense_forward(x, keys, batch, spatial):
     n, c = x.shape
     dense = torch.empty((batch, c) + tuple(spatial), dtype=torch.float32, device=x.device)
+    p = _profiler
+    e0 = p.begin() if p else None
     L.check(L.lib().scn_sparse_to_dense_forward(L.ptr(x), L.dtype_code(x), L.ptr(keys), n, c, batch, spatial[0],
                                                 spatial[1], spatial[2], L.ptr(dense), L.stream()),
             "scn_sparse_to_dense_forward")
+    if p:
+        p.end(e0, kind="sparse_to_dense_fwd", bytes=4.0 * dense.numel() + x.numel() * x.element_size())
     return dense
 
 
