@@ -145,7 +145,13 @@ int scn_rulebook_pairs(const int32_t* nbr, int K, int64_t n, int64_t n_pad, int3
  *   transpose=0: B_k = W[k] (Cin x Cout);  transpose=1: B_k = W[src]^T with src = mirror ? K-1-k : k.
  * Output element type follows precision (fp32 or bf16); n_in/n_out below are B_k's own dims. */
 int scn_conv_prep_weights(const float* W, int K, int Cin, int Cout, int transpose, int mirror,
-                          int precision, void* out, void* stream);
+                          int precision, int feat_dtype, void* out, void* stream);
+/* Which kernel family runs a (K, n_in, n_out) contraction for features of feat_dtype:
+ *   0 exact fp32 FMA (B_k fp32 [k][c][n]);  1 mma.sync tensor cores (B_k bf16 [k][n][c]);
+ *   2 tcgen05 tensor cores + TMEM (B_k as pre-swizzled 128-byte-row bf16 tiles).
+ * scn_conv_prep_bytes is the size of the buffer scn_conv_prep_weights fills for that path. */
+int scn_conv_path(int K, int n_in, int n_out, int precision, int feat_dtype);
+size_t scn_conv_prep_bytes(int K, int n_in, int n_out, int precision, int feat_dtype);
 
 /* in: [n_in_rows, n_in] of in_dtype; out: [n_out_rows, n_out] of out_dtype (fully overwritten);
  * nbr: [K][n_pad]; Bprep: output of scn_conv_prep_weights; bias: fp32 [n_out] or NULL. */
@@ -158,9 +164,7 @@ int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows, const int3
 int scn_conv_wgrad(const void* in, int in_dtype, const void* dout, int dout_dtype,
                    const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_in, int n_out,
                    int precision, float* dW, void* stream);
-/* 1 when (K, n_in, n_out, precision) runs on the tensor-core path (bf16 B_k), 0 when it takes the
- * exact fp32 FMA path (fp32 B_k): tells the caller how scn_conv_prep_weights laid B out. */
-int scn_conv_uses_tensor_cores(int K, int n_in, int n_out, int precision);
+
 
 /* dbias[c] = sum_rows dout[r][c]  (fp32 out, overwritten).  stats_ws: 2*C doubles of scratch. */
 int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out,

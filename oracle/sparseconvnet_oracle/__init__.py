@@ -48,7 +48,7 @@ def _rs(t):
 
 
 def _tensor_core_shape(k, n_in, n_out):
-    """Mirror of scn_conv_uses_tensor_cores(): only these shapes round their operands to bf16."""
+    """Mirror of scn_conv_path() > 0: only these shapes round their operands to bf16."""
     return n_in % 32 == 0 and n_out % 32 == 0 and n_in <= 256 and n_out <= 256 and k <= 128
 
 

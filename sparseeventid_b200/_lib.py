@@ -38,10 +38,11 @@ SIGNATURES = {
     "scn_rulebook_workspace": (_sz, [_i, _i64]),
     "scn_rulebook_count": (_i, [_p, _i, _i64, _i64, _p, _p]),
     "scn_rulebook_pairs": (_i, [_p, _i, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
-    "scn_conv_prep_weights": (_i, [_p, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "scn_conv_prep_weights": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "scn_conv_path": (_i, [_i, _i, _i, _i, _i]),
+    "scn_conv_prep_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "scn_conv_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p]),
     "scn_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i64, _i, _i, _i, _p, _p]),
-    "scn_conv_uses_tensor_cores": (_i, [_i, _i, _i, _i]),
     "scn_col_sum": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
     "scn_bn_forward": (_i, [_p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _p]),

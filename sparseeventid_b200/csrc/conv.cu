@@ -6,6 +6,14 @@
 // call sites src/networks/sparse_building_blocks.py:29-34,110-117,207-213).
 #include "common.cuh"
 
+// conv_tc.cu (tcgen05 path)
+bool scn_tc_disabled();
+bool scn_tc_shape_ok(int K, int n_in, int n_out);
+size_t scn_tc_image_bytes(int K, int n_in, int n_out);
+int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s);
+int scn_tc_forward(const __nv_bfloat16* in, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_in,
+                   int n_out, const void* bimg, const float* bias, __nv_bfloat16* out, cudaStream_t s);
+
 namespace {
 
 // =============================================================================================
@@ -467,18 +475,35 @@ int wgrad_generic_t(const TI* in, const TO* dout, const int32_t* nbr, int K, int
 
 }  // namespace
 
-extern "C" int scn_conv_uses_tensor_cores(int K, int n_in, int n_out, int precision) {
+// 0: exact fp32 FMA kernels; 1: mma.sync (HMMA) kernels, Bt[k][n][c] bf16; 2: tcgen05 kernel, swizzled image
+static int conv_path(int K, int n_in, int n_out, int precision, int feat_dtype) {
+  if (precision == SCN_PREC_BF16 && feat_dtype == SCN_BF16 && !scn_tc_disabled() && scn_tc_shape_ok(K, n_in, n_out))
+    return 2;
   return mma_ok(K, n_in, n_out, precision) ? 1 : 0;
 }
 
+extern "C" int scn_conv_path(int K, int n_in, int n_out, int precision, int feat_dtype) {
+  return conv_path(K, n_in, n_out, precision, feat_dtype);
+}
+
+extern "C" size_t scn_conv_prep_bytes(int K, int n_in, int n_out, int precision, int feat_dtype) {
+  switch (conv_path(K, n_in, n_out, precision, feat_dtype)) {
+    case 2: return scn_tc_image_bytes(K, n_in, n_out);
+    case 1: return (size_t)K * n_in * n_out * 2;
+    default: return (size_t)K * n_in * n_out * 4;
+  }
+}
+
 extern "C" int scn_conv_prep_weights(const float* W, int K, int Cin, int Cout, int transpose, int mirror,
-                                     int precision, void* out, void* stream) {
+                                     int precision, int feat_dtype, void* out, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!W || !out || K < 1 || Cin < 1 || Cout < 1) return SCN_ERR_ARG;
   const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
   int64_t total = (int64_t)K * Cin * Cout;
   unsigned g = grid_for(total, 256);
-  if (mma_ok(K, n_in, n_out, precision))
+  const int path = conv_path(K, n_in, n_out, precision, feat_dtype);
+  if (path == 2) return scn_tc_prep(W, K, Cin, Cout, transpose, mirror, out, s);
+  if (path == 1)
     k_prep_weights<__nv_bfloat16, 1><<<g, 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, (__nv_bfloat16*)out);
   else
     k_prep_weights<float, 0><<<g, 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, (float*)out);
@@ -494,6 +519,9 @@ extern "C" int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows,
   if (n_out_rows == 0) return SCN_OK;
   if (!in || !nbr || !Bprep || !out || K < 1 || n_pad < n_out_rows || (n_pad & 127)) return SCN_ERR_ARG;
   if (precision == SCN_PREC_FP32 && (in_dtype != SCN_F32 || out_dtype != SCN_F32)) return SCN_ERR_ARG;
+  if (in_dtype == out_dtype && conv_path(K, n_in, n_out, precision, in_dtype) == 2)
+    return scn_tc_forward((const __nv_bfloat16*)in, nbr, K, n_out_rows, n_pad, n_in, n_out, Bprep, bias,
+                          (__nv_bfloat16*)out, s);
   if (mma_ok(K, n_in, n_out, precision) && in_dtype == out_dtype) {
     if (in_dtype == SCN_F32)
       return conv_mma_t<float>((const float*)in, nbr, K, n_out_rows, n_pad, n_in, n_out, (const __nv_bfloat16*)Bprep,

@@ -27,7 +27,7 @@ class ConvFn(Function):
         prec = config.precision_code()
         w3 = _w3(weight)
         K, cin, cout = w3.shape
-        bprep = ops.prep_weights(w3, False, False, prec)
+        bprep = ops.prep_weights(w3, False, False, prec, config.feature_dtype())
         b = bias.detach().float().contiguous() if bias is not None else None
         out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, config.feature_dtype())
         ctx.save_for_backward(x, weight)
@@ -44,7 +44,7 @@ class ConvFn(Function):
         K, cin, cout = w3.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec)
+            bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec, x.dtype)
             dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
                                   kind="conv_dgrad")
         if ctx.needs_input_grad[1]:

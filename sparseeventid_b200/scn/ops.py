@@ -188,24 +188,28 @@ def rulebook_pairs(nbr: torch.Tensor, n: int):
 # ---------------------------------------------------------------------------- convolution
 
 
-def conv_uses_tc(K, n_in, n_out, prec) -> bool:
-    return bool(L.lib().scn_conv_uses_tensor_cores(K, n_in, n_out, prec))
+_DT = {torch.float32: L.SCN_F32, torch.bfloat16: L.SCN_BF16}
 
 
-def prep_weights(w3: torch.Tensor, transpose: bool, mirror: bool, prec: int) -> torch.Tensor:
-    """w3: fp32 [K, Cin, Cout] -> B_k laid out for the kernel that will run (bf16 Bt or fp32 B)."""
+def conv_path(K, n_in, n_out, prec, feat_dtype) -> int:
+    """0 = exact fp32 FMA kernels, 1 = mma.sync tensor cores, 2 = tcgen05 tensor cores (see scn_b200.h)."""
+    return int(L.lib().scn_conv_path(K, n_in, n_out, prec, _DT[feat_dtype]))
+
+
+def prep_weights(w3: torch.Tensor, transpose: bool, mirror: bool, prec: int, feat_dtype) -> torch.Tensor:
+    """w3: fp32 [K, Cin, Cout] -> B_k laid out for the kernel family that will run on feat_dtype features."""
     K, cin, cout = w3.shape
     n_in, n_out = (cout, cin) if transpose else (cin, cout)
-    tc = conv_uses_tc(K, n_in, n_out, prec)
-    out = torch.empty((K * cin * cout,), dtype=torch.bfloat16 if tc else torch.float32, device=w3.device)
-    L.check(L.lib().scn_conv_prep_weights(L.ptr(w3), K, cin, cout, int(transpose), int(mirror), prec, L.ptr(out),
-                                          L.stream()), "scn_conv_prep_weights")
+    nbytes = int(L.lib().scn_conv_prep_bytes(K, n_in, n_out, prec, _DT[feat_dtype]))
+    out = torch.empty((nbytes,), dtype=torch.uint8, device=w3.device)
+    L.check(L.lib().scn_conv_prep_weights(L.ptr(w3), K, cin, cout, int(transpose), int(mirror), prec, _DT[feat_dtype],
+                                          L.ptr(out), L.stream()), "scn_conv_prep_weights")
     return out
 
 
 def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, kind="conv_fwd") -> torch.Tensor:
     K, n_pad = nbr.shape
-    tc = conv_uses_tc(K, n_in, n_out, prec)
+    tc = conv_path(K, n_in, n_out, prec, out_dtype) > 0
     if tc and x.dtype != out_dtype:
         x = convert(x, out_dtype)
     out = torch.empty((n_out_rows, n_out), dtype=out_dtype, device=x.device)
@@ -221,7 +225,8 @@ def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, 
 
 def conv_wgrad(x, dout, nbr, n_rows, n_in, n_out, prec) -> torch.Tensor:
     K, n_pad = nbr.shape
-    if conv_uses_tc(K, n_in, n_out, prec) and x.dtype != dout.dtype:
+    tc = conv_path(K, n_in, n_out, prec, dout.dtype) > 0
+    if tc and x.dtype != dout.dtype:
         x = convert(x, dout.dtype)
     dw = torch.zeros((K, n_in, n_out), dtype=torch.float32, device=x.device)
     p = _profiler
@@ -229,8 +234,7 @@ def conv_wgrad(x, dout, nbr, n_rows, n_in, n_out, prec) -> torch.Tensor:
     L.check(L.lib().scn_conv_wgrad(L.ptr(x), L.dtype_code(x), L.ptr(dout), L.dtype_code(dout), L.ptr(nbr), K, n_rows,
                                    n_pad, n_in, n_out, prec, L.ptr(dw), L.stream()), "scn_conv_wgrad")
     if p:
-        p.end(e0, kind="conv_wgrad", K=K, n_in=n_in, n_out=n_out, rows_in=x.shape[0], rows_out=n_rows, nbr=nbr,
-              tc=conv_uses_tc(K, n_in, n_out, prec))
+        p.end(e0, kind="conv_wgrad", K=K, n_in=n_in, n_out=n_out, rows_in=x.shape[0], rows_out=n_rows, nbr=nbr, tc=tc)
     return dw
 
 
