@@ -11,8 +11,9 @@ bool scn_tc_disabled();
 bool scn_tc_shape_ok(int K, int n_in, int n_out);
 size_t scn_tc_image_bytes(int K, int n_in, int n_out);
 int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s);
-int scn_tc_forward(const __nv_bfloat16* in, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_in,
-                   int n_out, const void* bimg, const float* bias, __nv_bfloat16* out, cudaStream_t s);
+int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
+                   int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
+                   cudaStream_t s);
 
 namespace {
 
@@ -515,12 +516,11 @@ extern "C" int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows,
                                 int64_t n_out_rows, int64_t n_pad, int n_in, int n_out, const void* Bprep,
                                 const float* bias, int precision, void* out, int out_dtype, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  (void)n_in_rows;
   if (n_out_rows == 0) return SCN_OK;
   if (!in || !nbr || !Bprep || !out || K < 1 || n_pad < n_out_rows || (n_pad & 127)) return SCN_ERR_ARG;
   if (precision == SCN_PREC_FP32 && (in_dtype != SCN_F32 || out_dtype != SCN_F32)) return SCN_ERR_ARG;
   if (in_dtype == out_dtype && conv_path(K, n_in, n_out, precision, in_dtype) == 2)
-    return scn_tc_forward((const __nv_bfloat16*)in, nbr, K, n_out_rows, n_pad, n_in, n_out, Bprep, bias,
+    return scn_tc_forward((const __nv_bfloat16*)in, n_in_rows, nbr, K, n_out_rows, n_pad, n_in, n_out, Bprep, bias,
                           (__nv_bfloat16*)out, s);
   if (mma_ok(K, n_in, n_out, precision) && in_dtype == out_dtype) {
     if (in_dtype == SCN_F32)

@@ -1,17 +1,25 @@
 // Output-stationary gather-GEMM convolution on 5th-generation tensor cores (sm_100a only):
 //     out[o, :] = bias + sum_k  in[nbr[k][o], :] . B_k            (bf16 operands, fp32 accumulate)
-// One persistent CTA per SM walks 128-row output tiles.  Per (kernel offset k, 64-channel chunk):
-//   * 4 producer warps gather the 128 neighbour rows (16-byte cp.async, zero-fill for missing
-//     neighbours) into a 128B-swizzled K-major A tile in shared memory,
-//   * 1 thread streams the matching pre-swizzled weight tile B_k with a 1-D bulk async copy (TMA
-//     engine, mbarrier complete_tx),
+//
+// One persistent CTA per SM walks GROUPS of T 128-row output tiles (T * n_out <= 256 TMEM columns,
+// two groups double-buffered in the 512 columns).  The contraction (K offsets x n_in channels) is cut
+// into 64-channel pipeline stages (n_in == 32: two offsets share a stage).  For every stage q:
+//   * the weight tile B(q) (pre-swizzled image) is streamed ONCE per group by a 1-D bulk async copy
+//     (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
+//   * for each tile, 4 producer warps gather the 128 neighbour rows with 16-byte cp.async into a
+//     128B-swizzled K-major A tile; completion is signalled asynchronously
+//     (cp.async.mbarrier.arrive.noinc), so a thread runs a whole ring of stages ahead; rows whose
+//     neighbour is missing are zero-filled, and skipped outright when the slot already holds zeros,
 //   * 1 thread issues tcgen05.mma (M=128, N=n_out, K=16) accumulating in TMEM,
-//   * 4 epilogue warps drain the finished accumulator (tcgen05.ld), add bias, convert and store the
-//     tile while the next tile's MMAs run into the second TMEM buffer.
+//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store while
+//     the next group's MMAs run into the other TMEM half.
 // Every output row is written exactly once: no atomics, deterministic.
 // Replaces SCN's dConvolution_KMxKN_forwardA/B; reference call sites
 // src/networks/sparse_building_blocks.py:29-34,110-117.
+#include <cuda.h>      // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -21,12 +29,14 @@ constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int A_BYTES = BM * 128;       // 16 KB
 constexpr int EPI_WARPS = 4;            // warps 0..3  (TMEM lane quarter = warp index)
-constexpr int PROD_WARPS = 4;           // warps 4..7
-constexpr int WARP_MMA = 8;
-constexpr int WARP_BLOAD = 9;
-constexpr int THREADS = 320;
-constexpr int MAX_STAGES = 8;
-constexpr int LAG = 3;                  // cp.async groups kept in flight per producer thread
+constexpr int PROD_WARPS = 16;          // warps 4..19
+constexpr int PROD_THREADS = PROD_WARPS * 32;
+constexpr int WARP_MMA = 20;
+constexpr int WARP_BLOAD = 21;          // weight tiles
+constexpr int WARP_ILOAD = 22;          // neighbour-index blocks (separate thread: must never wait on the B ring)
+constexpr int THREADS = 736;
+constexpr int MAX_A = 12, MAX_B = 3, MAX_I = 3;   // ring depths: A tiles, B tiles, neighbour-index blocks
+constexpr int LAG = 6;                  // cp.async groups a producer thread keeps in flight before it signals
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -58,6 +68,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
+// long waits (epilogue warps idle through a whole group's main loop): back off so the spin does not
+// compete with the producer warps for issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(256);
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
@@ -73,6 +92,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// TMA tile::gather4: four rows (arbitrary row coordinates r0..r3, one box of 64 channels starting at column c)
+// of a 2-D tensor land as four consecutive 128-byte rows at dst, swizzled by the tensor map (SWIZZLE_128B);
+// rows/columns outside the tensor are zero-filled without touching memory.  512 bytes complete_tx on `bar`.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int c, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+      : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -117,39 +148,72 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 struct Params {
   const __nv_bfloat16* in;      // [n_in_rows, n_in]
   const int32_t* nbr;           // [K][n_pad]
-  const unsigned char* bimg;    // [K][nch][n_out][128 B] pre-swizzled weight tiles
+  const unsigned char* bimg;    // [Q][n_out][128 B] pre-swizzled weight tiles, one per stage
   const float* bias;            // [n_out] or null
   __nv_bfloat16* out;           // [n_rows, n_out]
   int64_t n_rows, n_pad;
-  int K, n_in, n_out, nch, last_kc, stages, num_tiles;
+  int K, n_in, n_out;
+  int pair;                     // n_in == 32: stage q holds offsets 2q and 2q+1 (32 channels each)
+  int nch, last_kc;             // !pair: chunks per offset, channels in the last chunk
+  int Q;                        // stages per tile
+  int T;                        // tiles per group
+  int SA, SB;                   // A / B ring depth
+  int num_tiles, num_groups;
+  int use_tma;                  // A tiles by TMA gather4 (1) or by cp.async (0)
+  int n_in_rows;                // rows of `in` (gather4: any row index >= n_in_rows is zero-filled)
 };
 
-__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
+constexpr int TMA_WARPS = 8;            // TMA mode: warps 4..11, lanes 0..3 each issue one gather4 per stage
+constexpr int TMA_LANES = 4;
+
+// PAIR: n_in == 32 (two offsets per stage).  NCH: 64-channel chunks per offset (ignored when PAIR).
+template <bool PAIR, int NCH>
+__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* gbase = smem_raw + (base - raw);
-  const int S = p.stages;
+  const int SA = p.SA, SB = p.SB;
   const uint32_t b_bytes = (uint32_t)p.n_out * 128u;
-  const uint32_t stage_bytes = A_BYTES + b_bytes;
-  const uint32_t bar0 = base + (uint32_t)S * stage_bytes;  // 8-byte aligned (stage_bytes % 1024 == 0)
-  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_STAGES + s); };
-  auto accf_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_STAGES + b); };
-  auto acce_bar = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_STAGES + 2 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (size_t)S * stage_bytes + 8 * (2 * MAX_STAGES + 4));
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + (uint32_t)SA * A_BYTES;
+  const uint32_t i_bytes = (uint32_t)(PAIR ? 2 : 1) * (uint32_t)p.T * 512u;   // one neighbour-index block
+  const uint32_t i_base = b_base + (uint32_t)SB * b_bytes;
+  const uint32_t bar0 = i_base + (uint32_t)MAX_I * i_bytes;  // 8-byte aligned
+  auto afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_A + s); };
+  auto bfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + s); };
+  auto bempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + MAX_B + s); };
+  auto ifull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + s); };
+  auto iempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + MAX_I + s); };
+  auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + b); };
+  auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 2 + b); };
+  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 4;
+  unsigned char* g_tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + (size_t)MAX_I * i_bytes + 8 * NBAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_tail);
+  const int* sidx_all = reinterpret_cast<const int*>(gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == WARP_MMA) {
     if (lane == 0) {
-      for (int s = 0; s < S; ++s) {
-        mbar_init(full_bar(s), PROD_WARPS + 1);   // 4 producer warps + the B loader's expect_tx arrival
-        mbar_init(empty_bar(s), 1);               // one tcgen05.commit
+      for (int s = 0; s < SA; ++s) {
+        // cp.async mode: one arrival per producer warp once its copies have landed;
+        // TMA mode: one arrive.expect_tx(512) per issuing lane, completed by the gather4 bytes
+        mbar_init(afull(s), p.use_tma ? TMA_WARPS * TMA_LANES : PROD_WARPS);
+        mbar_init(aempty(s), 1);                  // one tcgen05.commit
+      }
+      for (int s = 0; s < SB; ++s) {
+        mbar_init(bfull(s), 1);                   // the loader's expect_tx arrival (+ complete_tx bytes)
+        mbar_init(bempty(s), 1);
+      }
+      for (int s = 0; s < MAX_I; ++s) {
+        mbar_init(ifull(s), 1);
+        mbar_init(iempty(s), p.use_tma ? TMA_WARPS : PROD_WARPS);
       }
       for (int b = 0; b < 2; ++b) {
-        mbar_init(accf_bar(b), 1);
-        mbar_init(acce_bar(b), EPI_WARPS);
+        mbar_init(accf(b), 1);
+        mbar_init(acce(b), EPI_WARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -163,59 +227,164 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int my_tiles = (p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int stages_per_tile = p.K * p.nch;
+  const int my_groups = (p.num_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int Q = p.Q, T = p.T;
 
-  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    // ================================ A producers =========================================
-    const int r = (warp - EPI_WARPS) * 32 + lane;             // row of the tile owned by this thread
-    const uint32_t row_off = (uint32_t)r * 128u;
-    const uint32_t sw = (uint32_t)(r & 7);
-    uint32_t it = 0;                                           // stages issued by this thread
-    for (int t = 0; t < my_tiles; ++t) {
-      const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * BM + r;
-      int j_next = p.nbr[row];
-      for (int k = 0; k < p.K; ++k) {
-        const int j = j_next;
-        if (k + 1 < p.K) j_next = p.nbr[(int64_t)(k + 1) * p.n_pad + row];
-        const __nv_bfloat16* src_row = p.in + (int64_t)(j >= 0 ? j : 0) * p.n_in;
-        const int nbytes = j >= 0 ? 16 : 0;
-        for (int ch = 0; ch < p.nch; ++ch, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          mbar_wait(empty_bar(s), ((it / (uint32_t)S) & 1u) ^ 1u);
-          const uint32_t dst = base + (uint32_t)s * stage_bytes + row_off;
-          const int nchunk = (ch == p.nch - 1 ? p.last_kc : KC) >> 3;
-          const __nv_bfloat16* src = src_row + ch * KC;
-#pragma unroll 8
-          for (int c = 0; c < nchunk; ++c) cp_async16(dst + (((uint32_t)c ^ sw) << 4), src + c * 8, nbytes);
-          cp_async_commit();
-          if (it >= (uint32_t)LAG) {
-            cp_async_wait<LAG>();
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full_bar((int)((it - LAG) % (uint32_t)S)));
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS && p.use_tma) {
+    // ================================ A producers, TMA gather4 ==============================
+    // 8 warps x 4 lanes: lane (pw, l) owns tile rows [16pw + 4l, +4) and moves them with ONE gather4 per stage.
+    // Missing neighbours (-1) are turned into an out-of-range row, which the TMA engine zero-fills for free.
+    const int pw = warp - EPI_WARPS;
+    if (!PAIR && pw < TMA_WARPS && lane < TMA_LANES) {
+      const int r0 = pw * 16 + lane * 4;
+      const uint32_t dst_off = (uint32_t)r0 * 128u;
+      const int oob = p.n_in_rows;
+      int slot = 0, islot = 0;
+      uint32_t round = 0, iround = 0;
+      for (int g = 0; g < my_groups; ++g) {
+        const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
+        const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+        for (int step = 0; step < p.K; ++step) {
+          mbar_wait(ifull(islot), iround & 1u);
+          const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4);
+#pragma unroll
+          for (int chn = 0; chn < NCH; ++chn) {
+            for (int t = 0; t < T; ++t) {
+              int4 jj = make_int4(-1, -1, -1, -1);
+              if (t < tvalid) jj = *reinterpret_cast<const int4*>(sidx + t * 128 + r0);
+              jj.x = jj.x < 0 ? oob : jj.x; jj.y = jj.y < 0 ? oob : jj.y;
+              jj.z = jj.z < 0 ? oob : jj.z; jj.w = jj.w < 0 ? oob : jj.w;
+              mbar_wait(aempty(slot), (round & 1u) ^ 1u);
+              mbar_expect_tx(afull(slot), 512u);
+              tma_gather4(a_base + (uint32_t)slot * A_BYTES + dst_off, &tmap, chn * KC, jj.x, jj.y, jj.z, jj.w, afull(slot));
+              if (++slot == SA) { slot = 0; ++round; }
+            }
           }
+          __syncwarp(0xFu);
+          if (lane == 0) mbar_arrive(iempty(islot));
+          if (++islot == MAX_I) { islot = 0; ++iround; }
         }
       }
     }
-    // drain: everything issued has landed after wait_group 0
+  } else if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    // ================================ A producers, cp.async ================================
+    // Warp pw owns tile rows [8pw, 8pw+8).  In pass i (0..1) the 8 lanes with the same (lane >> 3) move one whole
+    // 128-byte row: lane handles 16-byte chunk (lane & 7) of row 8pw + 4i + (lane >> 3), so a warp-wide cp.async
+    // touches 4 contiguous 128-byte lines.  Missing neighbours are zero-filled by the same instruction
+    // (src-size 0: no global read).  Neighbour indices come from the shared-memory index ring, so one stage
+    // costs a thread: 1 barrier wait, 2 shared loads, 2 cp.async, 1 asynchronous arrive -- branch-free.
+    const int pw = warp - EPI_WARPS;
+    const int chunk = lane & 7;
+    const int sub = lane >> 3;
+    uint32_t dst_off[2];
+    int rowi[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int rt = pw * 8 + i * 4 + sub;                     // row within the tile
+      rowi[i] = rt;
+      dst_off[i] = (uint32_t)rt * 128u + (((uint32_t)chunk ^ (uint32_t)(rt & 7)) << 4);
+    }
+    const bool hi_half = PAIR && chunk >= 4;
+    const uint32_t col_bytes = PAIR ? (uint32_t)(chunk & 3) * 16u : (uint32_t)chunk * 16u;
+    const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
+    const unsigned char* in_bytes = reinterpret_cast<const unsigned char*>(p.in);
+    const int nsteps = PAIR ? Q : p.K;
+    int slot = 0, islot = 0, sig_slot = 0;
+    uint32_t round = 0, iround = 0, issued = 0;
+    for (int g = 0; g < my_groups; ++g) {
+      const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
+      const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+      for (int step = 0; step < nsteps; ++step) {
+        mbar_wait(ifull(islot), iround & 1u);
+        const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4) + (hi_half ? T * 128 : 0);
+        const bool half_dead = PAIR && hi_half && (2 * step + 1 >= p.K);
+#pragma unroll
+        for (int chn = 0; chn < (PAIR ? 1 : NCH); ++chn) {
+          const int nchunk = PAIR ? 8 : ((chn == NCH - 1 ? p.last_kc : KC) >> 3);
+          const bool lane_on = chunk < nchunk;                 // lanes past a 32-channel tail chunk stay idle
+          const uint32_t coff = col_bytes + (uint32_t)chn * 128u;
+          for (int t = 0; t < T; ++t) {
+            const bool tile_ok = t < tvalid && !half_dead;
+            int j[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) j[i] = tile_ok ? sidx[t * 128 + rowi[i]] : -1;
+            mbar_wait(aempty(slot), (round & 1u) ^ 1u);
+            const uint32_t abase = a_base + (uint32_t)slot * A_BYTES;
+            if (lane_on) {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const bool ok = j[i] >= 0;
+                const unsigned char* src = in_bytes + (ok ? (size_t)(uint32_t)j[i] * row_bytes + coff : (size_t)0);
+                cp_async16(abase + dst_off[i], src, ok ? 16 : 0);
+              }
+            }
+            cp_async_commit();
+            if (++slot == SA) { slot = 0; ++round; }
+            if (++issued > (uint32_t)LAG) {
+              // the stage issued LAG iterations ago has landed for this thread; once the whole warp agrees,
+              // publish it to the async proxy and signal the MMA thread (one arrival per warp)
+              cp_async_wait<LAG>();
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(afull(sig_slot));
+              if (++sig_slot == SA) sig_slot = 0;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(iempty(islot));
+        if (++islot == MAX_I) { islot = 0; ++iround; }
+      }
+    }
     cp_async_wait<0>();
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      const uint32_t first = it >= (uint32_t)LAG ? it - LAG : 0u;
-      for (uint32_t q = first; q < it; ++q) mbar_arrive(full_bar((int)(q % (uint32_t)S)));
+      const uint32_t left = issued < (uint32_t)LAG ? issued : (uint32_t)LAG;
+      for (uint32_t q2 = 0; q2 < left; ++q2) {
+        mbar_arrive(afull(sig_slot));
+        if (++sig_slot == SA) sig_slot = 0;
+      }
+    }
+  } else if (warp == WARP_ILOAD) {
+    // ================================ neighbour-index loader (1 thread) =====================
+    if (lane == 0) {
+      int islot = 0;
+      uint32_t iround = 0;
+      const int nsteps = PAIR ? Q : p.K;
+      for (int g = 0; g < my_groups; ++g) {
+        const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
+        const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+        const uint32_t blk = (uint32_t)tvalid * 512u;
+        for (int step = 0; step < nsteps; ++step) {
+          // indices of the group's tvalid*128 consecutive rows for this offset (pair: two offsets)
+          mbar_wait(iempty(islot), (iround & 1u) ^ 1u);
+          const uint32_t idst = i_base + (uint32_t)islot * i_bytes;
+          if (PAIR) {
+            const int k0 = 2 * step;
+            const bool two = k0 + 1 < p.K;
+            mbar_expect_tx(ifull(islot), two ? 2u * blk : blk);
+            bulk_g2s(idst, p.nbr + (int64_t)k0 * p.n_pad + tile0 * BM, blk, ifull(islot));
+            if (two) bulk_g2s(idst + (uint32_t)T * 512u, p.nbr + (int64_t)(k0 + 1) * p.n_pad + tile0 * BM, blk, ifull(islot));
+          } else {
+            mbar_expect_tx(ifull(islot), blk);
+            bulk_g2s(idst, p.nbr + (int64_t)step * p.n_pad + tile0 * BM, blk, ifull(islot));
+          }
+          if (++islot == MAX_I) { islot = 0; ++iround; }
+        }
+      }
     }
   } else if (warp == WARP_BLOAD) {
-    // ================================ B loader (1 thread) ===================================
+    // ================================ weight-tile loader (1 thread) =========================
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        for (int q = 0; q < stages_per_tile; ++q, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          mbar_wait(empty_bar(s), ((it / (uint32_t)S) & 1u) ^ 1u);
-          mbar_expect_tx(full_bar(s), b_bytes);
-          bulk_g2s(base + (uint32_t)s * stage_bytes + A_BYTES, p.bimg + (size_t)q * b_bytes, b_bytes, full_bar(s));
+      int bslot = 0;
+      uint32_t bround = 0;
+      for (int g = 0; g < my_groups; ++g) {
+        for (int q = 0; q < Q; ++q) {
+          mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
+          mbar_expect_tx(bfull(bslot), b_bytes);
+          bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)q * b_bytes, b_bytes, bfull(bslot));
+          if (++bslot == SB) { bslot = 0; ++bround; }
         }
       }
     }
@@ -223,55 +392,67 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     // ================================ MMA issuer (1 thread) =================================
     if (lane == 0) {
       const uint32_t idesc = make_idesc(p.n_out);
-      uint32_t it = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int buf = t & 1;
-        mbar_wait(acce_bar(buf), (((uint32_t)t >> 1) & 1u) ^ 1u);     // epilogue has drained this buffer
+      int aslot = 0, bslot = 0;
+      uint32_t around = 0, bround = 0;
+      for (int g = 0; g < my_groups; ++g) {
+        const int buf = g & 1;
+        mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);       // epilogue has drained this TMEM half
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
-        for (int q = 0; q < stages_per_tile; ++q, ++it) {
-          const int s = (int)(it % (uint32_t)S);
-          mbar_wait(full_bar(s), (it / (uint32_t)S) & 1u);
-          tc_fence_after();
-          const uint32_t a_addr = base + (uint32_t)s * stage_bytes;
-          const uint64_t da = make_desc_sw128(a_addr), db = make_desc_sw128(a_addr + A_BYTES);
-          const int ch = q % p.nch;
-          const int nk = (ch == p.nch - 1 ? p.last_kc : KC) >> 4;
-          for (int kk = 0; kk < nk; ++kk)
-            umma(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));                                   // frees the stage when the MMAs retire
+        for (int q = 0; q < Q; ++q) {
+          mbar_wait(bfull(bslot), bround & 1u);
+          const uint64_t db = make_desc_sw128(b_base + (uint32_t)bslot * b_bytes);
+          int nk;
+          if (PAIR) nk = 4;
+          else nk = ((q % NCH) == NCH - 1 ? p.last_kc : KC) >> 4;
+          for (int t = 0; t < T; ++t) {
+            mbar_wait(afull(aslot), around & 1u);
+            tc_fence_after();
+            const uint64_t da = make_desc_sw128(a_base + (uint32_t)aslot * A_BYTES);
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
+            for (int kk = 0; kk < nk; ++kk)
+              umma(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u);
+            umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
+            if (++aslot == SA) { aslot = 0; ++around; }
+          }
+          umma_commit(bempty(bslot));
+          if (++bslot == SB) { bslot = 0; ++bround; }
         }
-        umma_commit(accf_bar(buf));                                    // accumulator complete
+        umma_commit(accf(buf));                                      // the group's accumulators are complete
       }
     }
   } else {
     // ================================ epilogue (warps 0..3) ==================================
-    for (int t = 0; t < my_tiles; ++t) {
-      const int buf = t & 1;
-      mbar_wait(accf_bar(buf), ((uint32_t)t >> 1) & 1u);
+    for (int g = 0; g < my_groups; ++g) {
+      const int buf = g & 1;
+      mbar_wait_sleep(accf(buf), ((uint32_t)g >> 1) & 1u);
       tc_fence_after();
-      const int64_t row = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * BM + warp * 32 + lane;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 256u;
-      for (int c0 = 0; c0 < p.n_out; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + (uint32_t)c0, v);
-        if (row < p.n_rows) {
-          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.n_out + c0);
+      for (int t = 0; t < T; ++t) {
+        const int64_t tile = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T + t;
+        if (tile >= p.num_tiles) break;
+        const int64_t row = tile * BM + warp * 32 + lane;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
+        for (int c0 = 0; c0 < p.n_out; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          if (row < p.n_rows) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.n_out + c0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float f[8];
+            for (int gq = 0; gq < 4; ++gq) {
+              float f[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[g * 8 + e]) + (p.bias ? __ldg(p.bias + c0 + g * 8 + e) : 0.f);
-            uint4 u;
-            u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-            u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
-            dst[g] = u;
+              for (int e = 0; e < 8; ++e)
+                f[e] = __uint_as_float(v[gq * 8 + e]) + (p.bias ? __ldg(p.bias + c0 + gq * 8 + e) : 0.f);
+              uint4 u;
+              u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+              u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+              dst[gq] = u;
+            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acce_bar(buf));
+      if (lane == 0) mbar_arrive(acce(buf));
     }
   }
 
@@ -283,10 +464,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   }
 }
 
-// Weight image for the kernel above: tile (k, ch) = n_out rows of 128 bytes, 16-byte chunk c of row n
-// stored at chunk position c ^ (n & 7)  (the SWIZZLE_128B pattern); unused half rows stay zero.
+// Weight image: one tile per stage q = n_out rows of 128 bytes; 16-byte chunk c of row n is stored at
+// chunk position c ^ (n & 7) (the SWIZZLE_128B pattern); unused parts stay zero.
+//   pair  (n_in == 32): q = k/2, chunk = (k&1)*4 + c/8
+//   !pair             : q = k*nch + c/64, chunk = (c%64)/8
 __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, int Cout, int transpose, int mirror,
-                                  int nch, __nv_bfloat16* __restrict__ img) {
+                                  int nch, int pair, __nv_bfloat16* __restrict__ img) {
   const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
   int64_t total = (int64_t)K * n_in * n_out;
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -297,12 +480,47 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
   int src_k = (transpose && mirror) ? K - 1 - k : k;
   int ci = transpose ? n : c, co = transpose ? c : n;
   float v = W[((int64_t)src_k * Cin + ci) * Cout + co];
-  int ch = c / KC, cc = c % KC;
-  size_t off = (((size_t)k * nch + ch) * n_out + n) * 64 + (size_t)(((cc >> 3) ^ (n & 7)) << 3) + (cc & 7);
+  int q, chunk;
+  if (pair) { q = k >> 1; chunk = (k & 1) * 4 + (c >> 3); }
+  else { q = k * nch + c / KC; chunk = (c % KC) >> 3; }
+  size_t off = ((size_t)q * n_out + n) * 64 + (size_t)((chunk ^ (n & 7)) << 3) + (c & 7);
   img[off] = __float2bfloat16_rn(v);
 }
 
+static int stages_per_tile(int K, int n_in, bool pair) {
+  if (pair) return (K + 1) / 2;
+  return K * ((n_in + KC - 1) / KC);
+}
+
 }  // namespace tc
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tc_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  }
+  return fn;
+}
+// 0: cp.async gather (default), 1: TMA tile::gather4 (SCN_B200_TC_GATHER=tma).  Measured on B200 (profiles/):
+// one gather4 moves only 512 bytes and costs ~77 cycles of issue per SM, i.e. ~6.6 B/clk/SM, against ~16 B/clk/SM
+// for 16-byte cp.async -- so the TMA path, although it zero-fills missing rows for free, is kept as an option only.
+static int tc_gather_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SCN_B200_TC_GATHER");
+    v = (e && std::strcmp(e, "tma") == 0) ? 1 : 0;
+  }
+  return v;
+}
 
 bool scn_tc_disabled() {
   static int v = -1;
@@ -317,39 +535,88 @@ bool scn_tc_shape_ok(int K, int n_in, int n_out) {
   return K >= 1 && (n_in % 32) == 0 && (n_out % 32) == 0 && n_in >= 32 && n_in <= 256 && n_out >= 32 && n_out <= 256;
 }
 
+// two offsets share a stage only in cp.async mode (the TMA box is one source row wide)
+static bool tc_pair(int n_in) { return n_in == 32 && (tc_gather_mode() == 0 || tc_encoder() == nullptr); }
+
 size_t scn_tc_image_bytes(int K, int n_in, int n_out) {
-  int nch = (n_in + tc::KC - 1) / tc::KC;
-  return (size_t)K * nch * n_out * 128;
+  return (size_t)tc::stages_per_tile(K, n_in, tc_pair(n_in)) * n_out * 128;
 }
 
 int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s) {
   const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
   const int nch = (n_in + tc::KC - 1) / tc::KC;
-  if (n_in % tc::KC) SCN_CUDA(cudaMemsetAsync(out, 0, scn_tc_image_bytes(K, n_in, n_out), s));
+  const int pair = tc_pair(n_in) ? 1 : 0;
+  if ((n_in % tc::KC) != 0) SCN_CUDA(cudaMemsetAsync(out, 0, scn_tc_image_bytes(K, n_in, n_out), s));
   int64_t total = (int64_t)K * Cin * Cout;
-  tc::k_prep_weights_tc<<<grid_for(total, 256), 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, nch,
+  tc::k_prep_weights_tc<<<grid_for(total, 256), 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, nch, pair,
                                                              (__nv_bfloat16*)out);
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }
 
-int scn_tc_forward(const __nv_bfloat16* in, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_in,
-                   int n_out, const void* bimg, const float* bias, __nv_bfloat16* out, cudaStream_t s) {
+int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
+                   int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
+                   cudaStream_t s) {
   tc::Params p;
+  CUtensorMap tmap;
+  std::memset(&tmap, 0, sizeof(tmap));
+  p.use_tma = 0;
+  p.n_in_rows = (int)n_in_rows;
+  if (tc_gather_mode() == 1 && tc_encoder() != nullptr && n_in_rows > 0 && n_in_rows < 0x7fffffffLL) {
+    const cuuint64_t gdim[2] = {(cuuint64_t)n_in, (cuuint64_t)n_in_rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)n_in * 2u};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::KC, 1u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = tc_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(in), gdim, gstride,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return SCN_ERR_UNSUPPORTED;
+    p.use_tma = 1;
+  }
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
+  p.pair = tc_pair(n_in) ? 1 : 0;
   p.nch = (n_in + tc::KC - 1) / tc::KC;
   p.last_kc = n_in - (p.nch - 1) * tc::KC;
-  const uint32_t stage_bytes = tc::A_BYTES + (uint32_t)n_out * 128u;
-  int stages = (int)((200u * 1024u) / stage_bytes);
-  if (stages > tc::MAX_STAGES) stages = tc::MAX_STAGES;
-  if (stages < tc::LAG + 1) return SCN_ERR_UNSUPPORTED;
-  p.stages = stages;
+  p.Q = tc::stages_per_tile(K, n_in, p.pair != 0);
   p.num_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-  size_t smem = 1024 + (size_t)stages * stage_bytes + 8 * (2 * tc::MAX_STAGES + 4) + 16;
-  SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
-  tc::k_conv_tc<<<grid, tc::THREADS, smem, s>>>(p);
-  SCN_LAUNCH_CHECK();
-  return SCN_OK;
+  // tiles per group: as many accumulators as fit in half of TMEM, but keep every SM busy
+  int tmax = 256 / n_out;
+  if (tmax < 1) tmax = 1;
+  int T = 1;
+  long best = -1;
+  for (int cand = tmax; cand >= 1; --cand) {
+    long groups = (p.num_tiles + cand - 1) / cand;
+    long busiest = ((groups + kNumSMs - 1) / kNumSMs) * cand;     // tiles walked by the busiest CTA
+    if (best < 0 || busiest < best) { best = busiest; T = cand; }
+  }
+  p.T = T;
+  p.num_groups = (p.num_tiles + T - 1) / T;
+  const uint32_t b_bytes = (uint32_t)n_out * 128u;
+  p.SB = T > 1 ? 3 : 2;
+  if (p.SB > tc::MAX_B) p.SB = tc::MAX_B;
+  const uint32_t i_bytes = (uint32_t)(p.pair ? 2 : 1) * (uint32_t)T * 512u;
+  constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 2 * tc::MAX_I + 4;
+  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + (uint32_t)tc::MAX_I * i_bytes + 8u * NBAR + 16u;
+  const uint32_t budget = 220u * 1024u;
+  int SA = (int)((budget - fixed) / tc::A_BYTES);
+  if (SA > tc::MAX_A) SA = tc::MAX_A;
+  if (SA < tc::LAG + 2) return SCN_ERR_UNSUPPORTED;
+  p.SA = SA;
+  size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
+  int grid = p.num_groups < kNumSMs ? p.num_groups : kNumSMs;
+  auto launch = [&](auto kern) -> int {
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, tc::THREADS, smem, s>>>(p, tmap);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  };
+  if (p.pair) return launch(tc::k_conv_tc<true, 1>);
+  switch (p.nch) {
+    case 1: return launch(tc::k_conv_tc<false, 1>);
+    case 2: return launch(tc::k_conv_tc<false, 2>);
+    case 3: return launch(tc::k_conv_tc<false, 3>);
+    case 4: return launch(tc::k_conv_tc<false, 4>);
+    default: return SCN_ERR_UNSUPPORTED;
+  }
 }
