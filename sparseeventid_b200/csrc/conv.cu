@@ -60,6 +60,37 @@ __global__ void k_conv_generic(const TI* __restrict__ in, const int32_t* __restr
   Elem<TO>::st(out + idx, acc);
 }
 
+// Single input channel (the 5x5x5 / 1x5x5 stem, reference src/networks/resnet.py:30-36,44-50): a K-tap stencil on
+// a scalar field -- pure bandwidth.  One thread per output row keeps all NOUT accumulators in registers, reads its
+// K neighbour indices (coalesced across the warp) and the weights from shared memory (broadcast).
+template <typename TI, typename TO, int NOUT>
+__global__ void __launch_bounds__(256) k_conv_cin1(const TI* __restrict__ in, const int32_t* __restrict__ nbr, int K,
+                                                   int64_t n_rows, int64_t n_pad, const float* __restrict__ B,
+                                                   const float* __restrict__ bias, TO* __restrict__ out) {
+  extern __shared__ float s_w[];          // [K][NOUT]
+  for (int i = threadIdx.x; i < K * NOUT; i += blockDim.x) s_w[i] = B[i];
+  __syncthreads();
+  const int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (o >= n_rows) return;
+  float acc[NOUT];
+#pragma unroll
+  for (int c = 0; c < NOUT; ++c) acc[c] = bias ? bias[c] : 0.f;
+  int j = nbr[o];
+  for (int k = 0; k < K; ++k) {
+    const int jn = k + 1 < K ? nbr[(int64_t)(k + 1) * n_pad + o] : -1;
+    if (j >= 0) {
+      const float v = Elem<TI>::ld(in + j);
+      const float* w = s_w + k * NOUT;
+#pragma unroll
+      for (int c = 0; c < NOUT; ++c) acc[c] = fmaf(v, w[c], acc[c]);
+    }
+    j = jn;
+  }
+  TO* dst = out + o * NOUT;
+#pragma unroll
+  for (int c = 0; c < NOUT; c += 4) st4(dst + c, make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]));
+}
+
 // dW[k][c][n] += sum over rows o of the chunk with nbr[k][o] >= 0 of in[nbr][c] * dout[o][n]
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_wgrad_generic(const TI* __restrict__ in, const TO* __restrict__ dout,
@@ -457,6 +488,15 @@ int wgrad_mma_t(const T* in, const T* dout, const int32_t* nbr, int K, int64_t n
 template <typename TI, typename TO>
 int conv_generic_t(const TI* in, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_in, int n_out,
                    const float* B, const float* bias, TO* out, cudaStream_t s) {
+  if (n_in == 1 && (n_out == 16 || n_out == 32 || n_out == 64) && (size_t)K * n_out * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)K * n_out * sizeof(float);
+    const unsigned g = grid_for(n_rows, 256);
+    if (n_out == 16) k_conv_cin1<TI, TO, 16><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
+    else if (n_out == 32) k_conv_cin1<TI, TO, 32><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
+    else k_conv_cin1<TI, TO, 64><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   k_conv_generic<TI, TO><<<grid_for(n_rows * n_out, 256), 256, 0, s>>>(in, nbr, K, n_rows, n_pad, n_in, n_out, B, bias,
                                                                        out);
   SCN_LAUNCH_CHECK();

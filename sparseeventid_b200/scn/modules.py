@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from . import config, ops
+from . import config, dense_view, ops
 from . import functional as F
 from .core import Metadata, SparseConvNetTensor, as_tuple
 
@@ -271,8 +271,14 @@ class SparseToDense(nn.Module):
         sp = input._sp()
         lvl = md.levels[sp]
         sp3 = tuple(sp) + (1,) * (3 - len(sp))
-        dense = F.SparseToDenseFn.apply(input.features, lvl.keys, md.batch_size, sp3)
-        return dense.view((md.batch_size, input.features.shape[1]) + tuple(sp))
+        batch, c = md.batch_size, input.features.shape[1]
+
+        def materialize(feats):
+            return F.SparseToDenseFn.apply(feats, lvl.keys, batch, sp3).view((batch, c) + tuple(sp))
+        if dense_view.lazy_dense_enabled():
+            # the dense tensor to every consumer, but tanh / full-extent average pooling run on the rows
+            return dense_view.SparseDenseTensor(input.features, lvl.keys, batch, tuple(sp), materialize)
+        return materialize(input.features)
 
 
 class Sequential(nn.Sequential):
