@@ -263,14 +263,15 @@ def run_ours(args, rank, world, local_rank):
     e2e = args.batch * world * args.steps / (ms_e2e * 1e-3)
 
     # ---- instrumented pass (rank 0): CUDA events around every launch of this library's hot kernels
+    # (every rank runs the two extra steps -- they contain the gradient all-reduce -- only rank 0 records)
     roof, breakdown = None, None
+    prof = ops.Profiler() if rank == 0 else None
+    ops.set_profiler(prof)
+    for i in range(2):
+        step_resident(i)
+    ops.set_profiler(None)
+    barrier()
     if rank == 0:
-        prof = ops.Profiler()
-        ops.set_profiler(prof)
-        for i in range(2):
-            step_resident(i)
-        ops.set_profiler(None)
-        torch.cuda.synchronize()
         recs = prof.finish()
         eb = 2 if args.precision == "bf16" else 4
         agg = {}

@@ -3,17 +3,22 @@
 //
 // One persistent CTA per SM walks GROUPS of T 128-row output tiles (T * n_out <= 256 TMEM columns,
 // two groups double-buffered in the 512 columns).  The contraction (K offsets x n_in channels) is cut
-// into 64-channel pipeline stages (n_in == 32: two offsets share a stage).  For every stage q:
-//   * the weight tile B(q) (pre-swizzled image) is streamed ONCE per group by a 1-D bulk async copy
-//     (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
-//   * for each tile, 4 producer warps gather the 128 neighbour rows with 16-byte cp.async into a
-//     128B-swizzled K-major A tile; completion is signalled asynchronously
-//     (cp.async.mbarrier.arrive.noinc), so a thread runs a whole ring of stages ahead; rows whose
-//     neighbour is missing are zero-filled, and skipped outright when the slot already holds zeros,
+// into stages of 64 channels (one 128-byte shared-memory row).  For every stage q = (offset, chunk):
+//   * the weight tile B(q) (n_out x 128 B, pre-swizzled image) is streamed ONCE per group by a 1-D bulk
+//     async copy (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group; the group's
+//     T*128 neighbour indices arrive the same way into an index ring,
+//   * for each tile, 8 producer warps gather the 128 neighbour rows into a 128B-swizzled K-major A tile:
+//     8 lanes move one 128-byte row (coalesced 16-byte LDG), the loads of D stages are in flight per thread
+//     before the first is stored (STS.128), missing neighbours are written as zeros without a global read,
 //   * 1 thread issues tcgen05.mma (M=128, N=n_out, K=16) accumulating in TMEM,
-//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store while
-//     the next group's MMAs run into the other TMEM half.
+//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store while the
+//     next group's MMAs run into the other TMEM half.
 // Every output row is written exactly once: no atomics, deterministic.
+//
+// Measured alternatives for the A gather (profiles/): 16-byte cp.async tops out near
+// 16 B/clk/SM (~950 cycles per 16 KB stage); TMA tile::gather4 (kept as an option, SCN_B200_TC_GATHER=tma)
+// costs ~77 cycles per 512-byte instruction.  LDG.128 + STS.128 is the fastest of the three.
+//
 // Replaces SCN's dConvolution_KMxKN_forwardA/B; reference call sites
 // src/networks/sparse_building_blocks.py:29-34,110-117.
 #include <cuda.h>      // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
@@ -29,14 +34,14 @@ constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int A_BYTES = BM * 128;       // 16 KB
 constexpr int EPI_WARPS = 4;            // warps 0..3  (TMEM lane quarter = warp index)
-constexpr int PROD_WARPS = 16;          // warps 4..19
-constexpr int PROD_THREADS = PROD_WARPS * 32;
-constexpr int WARP_MMA = 20;
-constexpr int WARP_BLOAD = 21;          // weight tiles
-constexpr int WARP_ILOAD = 22;          // neighbour-index blocks (separate thread: must never wait on the B ring)
-constexpr int THREADS = 736;
-constexpr int MAX_A = 12, MAX_B = 3, MAX_I = 3;   // ring depths: A tiles, B tiles, neighbour-index blocks
-constexpr int LAG = 6;                  // cp.async groups a producer thread keeps in flight before it signals
+constexpr int PROD_WARPS = 8;           // warps 4..11
+constexpr int WARP_MMA = 12;
+constexpr int WARP_BLOAD = 13;          // weight tiles
+constexpr int WARP_ILOAD = 14;          // neighbour-index blocks (separate thread: must never wait on the B ring)
+constexpr int THREADS = 480;
+constexpr int MAX_A = 12, MAX_B = 6, MAX_I = 4;   // ring depths: A tiles, B tiles, neighbour-index blocks
+constexpr int D = 4;                    // stages whose global loads a producer thread keeps in flight
+constexpr int TMA_LANES = 4;            // TMA mode: lanes 0..3 of each producer warp issue one gather4 per stage
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,16 +82,33 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+// Warp-uniform leader election.  The issuing warps keep their whole control flow warp-uniform and only predicate
+// the tcgen05 / bulk-copy instruction itself on the elected lane: operands then live in uniform registers.  (With an
+// `if (lane == 0)` around the loop the compiler cannot prove uniformity and wraps every UTCHMMA / UTCBAR / UBLKCP in
+// an R2UR + ELECT + BRA.U.ANY waterfall: ~80 cycles each, which made the single MMA thread the bottleneck.)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 ldg_nc128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -148,26 +170,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 struct Params {
   const __nv_bfloat16* in;      // [n_in_rows, n_in]
   const int32_t* nbr;           // [K][n_pad]
-  const unsigned char* bimg;    // [Q][n_out][128 B] pre-swizzled weight tiles, one per stage
+  const unsigned char* bimg;    // [K*nch][n_out][128 B] pre-swizzled weight tiles, one per stage
   const float* bias;            // [n_out] or null
   __nv_bfloat16* out;           // [n_rows, n_out]
   int64_t n_rows, n_pad;
   int K, n_in, n_out;
-  int pair;                     // n_in == 32: stage q holds offsets 2q and 2q+1 (32 channels each)
-  int nch, last_kc;             // !pair: chunks per offset, channels in the last chunk
-  int Q;                        // stages per tile
+  int last_kc;                  // channels in the last 64-channel chunk of an offset (64 or 32)
   int T;                        // tiles per group
   int SA, SB;                   // A / B ring depth
   int num_tiles, num_groups;
-  int use_tma;                  // A tiles by TMA gather4 (1) or by cp.async (0)
+  int use_tma;                  // A tiles by TMA gather4 (1) or by LDG+STS (0)
   int n_in_rows;                // rows of `in` (gather4: any row index >= n_in_rows is zero-filled)
 };
 
-constexpr int TMA_WARPS = 8;            // TMA mode: warps 4..11, lanes 0..3 each issue one gather4 per stage
-constexpr int TMA_LANES = 4;
-
-// PAIR: n_in == 32 (two offsets per stage).  NCH: 64-channel chunks per offset (ignored when PAIR).
-template <bool PAIR, int NCH>
+// NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
+// 32 channels each (chunks 0-3 from offset 2q, chunks 4-7 from offset 2q+1), halving the stage count.
+template <int NCH, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -177,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   const uint32_t b_bytes = (uint32_t)p.n_out * 128u;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)SA * A_BYTES;
-  const uint32_t i_bytes = (uint32_t)(PAIR ? 2 : 1) * (uint32_t)p.T * 512u;   // one neighbour-index block
+  const uint32_t i_bytes = (uint32_t)(PAIR ? 2 : 1) * (uint32_t)p.T * 512u;   // index block: T tiles x 128 rows (x2 offsets)
   const uint32_t i_base = b_base + (uint32_t)SB * b_bytes;
   const uint32_t bar0 = i_base + (uint32_t)MAX_I * i_bytes;  // 8-byte aligned
   auto afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -189,8 +207,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + b); };
   auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 2 + b); };
   constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 4;
-  unsigned char* g_tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + (size_t)MAX_I * i_bytes + 8 * NBAR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_tail);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes +
+                                                    (size_t)MAX_I * i_bytes + 8 * NBAR);
   const int* sidx_all = reinterpret_cast<const int*>(gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -198,9 +216,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) {
-        // cp.async mode: one arrival per producer warp once its copies have landed;
+        // LDG/STS mode: one arrival per producer warp once its rows are stored and fenced;
         // TMA mode: one arrive.expect_tx(512) per issuing lane, completed by the gather4 bytes
-        mbar_init(afull(s), p.use_tma ? TMA_WARPS * TMA_LANES : PROD_WARPS);
+        mbar_init(afull(s), p.use_tma ? PROD_WARPS * TMA_LANES : PROD_WARPS);
         mbar_init(aempty(s), 1);                  // one tcgen05.commit
       }
       for (int s = 0; s < SB; ++s) {
@@ -209,7 +227,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
       }
       for (int s = 0; s < MAX_I; ++s) {
         mbar_init(ifull(s), 1);
-        mbar_init(iempty(s), p.use_tma ? TMA_WARPS : PROD_WARPS);
+        mbar_init(iempty(s), PROD_WARPS);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(accf(b), 1);
@@ -228,14 +246,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   const uint32_t tmem_base = *tmem_slot;
 
   const int my_groups = (p.num_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int Q = p.Q, T = p.T;
+  const int T = p.T;
+  const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // index blocks per tile
+  const int Q = NSTEP * NCH;                                // stages per tile
 
-  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS && p.use_tma) {
-    // ================================ A producers, TMA gather4 ==============================
-    // 8 warps x 4 lanes: lane (pw, l) owns tile rows [16pw + 4l, +4) and moves them with ONE gather4 per stage.
-    // Missing neighbours (-1) are turned into an out-of-range row, which the TMA engine zero-fills for free.
+  if (!PAIR && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS && p.use_tma) {
+    // ================================ A producers, TMA gather4 (option) =====================
+    // lane (pw, l < 4) owns tile rows [16pw + 4l, +4) and moves them with ONE gather4 per stage.  Missing
+    // neighbours (-1) become an out-of-range row index, which the TMA engine zero-fills without reading.
     const int pw = warp - EPI_WARPS;
-    if (!PAIR && pw < TMA_WARPS && lane < TMA_LANES) {
+    if (lane < TMA_LANES) {
       const int r0 = pw * 16 + lane * 4;
       const uint32_t dst_off = (uint32_t)r0 * 128u;
       const int oob = p.n_in_rows;
@@ -260,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
               if (++slot == SA) { slot = 0; ++round; }
             }
           }
+          // the index block is released by lane 0 of every producer warp (count = PROD_WARPS)
           __syncwarp(0xFu);
           if (lane == 0) mbar_arrive(iempty(islot));
           if (++islot == MAX_I) { islot = 0; ++iround; }
@@ -267,160 +288,177 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
       }
     }
   } else if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    // ================================ A producers, cp.async ================================
-    // Warp pw owns tile rows [8pw, 8pw+8).  In pass i (0..1) the 8 lanes with the same (lane >> 3) move one whole
-    // 128-byte row: lane handles 16-byte chunk (lane & 7) of row 8pw + 4i + (lane >> 3), so a warp-wide cp.async
-    // touches 4 contiguous 128-byte lines.  Missing neighbours are zero-filled by the same instruction
-    // (src-size 0: no global read).  Neighbour indices come from the shared-memory index ring, so one stage
-    // costs a thread: 1 barrier wait, 2 shared loads, 2 cp.async, 1 asynchronous arrive -- branch-free.
+    // ================================ A producers, LDG.128 -> STS.128 ========================
+    // Warp pw owns tile rows [16pw, 16pw+16).  In pass i (0..3) the 8 lanes with the same (lane >> 3) move one
+    // whole 128-byte row: lane handles 16-byte chunk (lane & 7) of row 16pw + 4i + (lane >> 3), so a warp-wide
+    // load touches 4 contiguous 128-byte lines.  Work is done in batches of D stages: first all global loads of
+    // the batch are issued (the neighbour indices come from the shared-memory ring; no waiting on free A slots),
+    // then each stage is stored to its slot as soon as the slot is free, fenced for the async proxy (tensor
+    // core reads) and signalled with ONE mbarrier arrival per warp.
     const int pw = warp - EPI_WARPS;
     const int chunk = lane & 7;
     const int sub = lane >> 3;
-    uint32_t dst_off[2];
-    int rowi[2];
+    uint32_t dst_off[4];
+    int rowi[4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int rt = pw * 8 + i * 4 + sub;                     // row within the tile
+    for (int i = 0; i < 4; ++i) {
+      const int rt = pw * 16 + i * 4 + sub;                    // row within the tile
       rowi[i] = rt;
       dst_off[i] = (uint32_t)rt * 128u + (((uint32_t)chunk ^ (uint32_t)(rt & 7)) << 4);
     }
-    const bool hi_half = PAIR && chunk >= 4;
+    const bool hi_half = PAIR && chunk >= 4;                   // this lane's 16 bytes belong to offset 2q+1
     const uint32_t col_bytes = PAIR ? (uint32_t)(chunk & 3) * 16u : (uint32_t)chunk * 16u;
     const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
     const unsigned char* in_bytes = reinterpret_cast<const unsigned char*>(p.in);
-    const int nsteps = PAIR ? Q : p.K;
-    int slot = 0, islot = 0, sig_slot = 0;
-    uint32_t round = 0, iround = 0, issued = 0;
-    for (int g = 0; g < my_groups; ++g) {
-      const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
-      const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-      for (int step = 0; step < nsteps; ++step) {
-        mbar_wait(ifull(islot), iround & 1u);
-        const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4) + (hi_half ? T * 128 : 0);
-        const bool half_dead = PAIR && hi_half && (2 * step + 1 >= p.K);
+    const int last_chunks = p.last_kc >> 3;
+
+    // issue cursor over (group, offset, chunk, tile)
+    int cg = 0, ck = 0, cc = 0, ct = 0;
+    int tvalid;
+    {
+      const int64_t tile0 = (int64_t)blockIdx.x * T;
+      tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+    }
+    int islot = 0, slot = 0;
+    uint32_t iround = 0, round = 0;
+    int64_t remaining = (int64_t)my_groups * Q * T;
+    while (remaining > 0) {
+      const int nb = remaining < D ? (int)remaining : D;
+      uint4 v[D][4];
+      // ---- phase 1: issue the global loads of up to D stages -------------------------------------------
 #pragma unroll
-        for (int chn = 0; chn < (PAIR ? 1 : NCH); ++chn) {
-          const int nchunk = PAIR ? 8 : ((chn == NCH - 1 ? p.last_kc : KC) >> 3);
-          const bool lane_on = chunk < nchunk;                 // lanes past a 32-channel tail chunk stay idle
-          const uint32_t coff = col_bytes + (uint32_t)chn * 128u;
-          for (int t = 0; t < T; ++t) {
-            const bool tile_ok = t < tvalid && !half_dead;
-            int j[2];
+      for (int d = 0; d < D; ++d) {
+        if (d < nb) {
+          if (cc == 0 && ct == 0) mbar_wait(ifull(islot), iround & 1u);      // first stage of an offset
+          const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4) + ct * 128 + (hi_half ? T * 128 : 0);
+          const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
+          const uint32_t coff = col_bytes + (uint32_t)cc * 128u;
+          const bool tile_ok = ct < tvalid && !(hi_half && 2 * ck + 1 >= p.K);
 #pragma unroll
-            for (int i = 0; i < 2; ++i) j[i] = tile_ok ? sidx[t * 128 + rowi[i]] : -1;
-            mbar_wait(aempty(slot), (round & 1u) ^ 1u);
-            const uint32_t abase = a_base + (uint32_t)slot * A_BYTES;
-            if (lane_on) {
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const bool ok = j[i] >= 0;
-                const unsigned char* src = in_bytes + (ok ? (size_t)(uint32_t)j[i] * row_bytes + coff : (size_t)0);
-                cp_async16(abase + dst_off[i], src, ok ? 16 : 0);
-              }
-            }
-            cp_async_commit();
-            if (++slot == SA) { slot = 0; ++round; }
-            if (++issued > (uint32_t)LAG) {
-              // the stage issued LAG iterations ago has landed for this thread; once the whole warp agrees,
-              // publish it to the async proxy and signal the MMA thread (one arrival per warp)
-              cp_async_wait<LAG>();
-              fence_proxy_async();
+          for (int i = 0; i < 4; ++i) {
+            const int j = tile_ok ? sidx[rowi[i]] : -1;
+            v[d][i] = make_uint4(0u, 0u, 0u, 0u);
+            if (j >= 0 && lane_on) v[d][i] = ldg_nc128(in_bytes + ((size_t)(uint32_t)j * row_bytes + coff));
+          }
+          // advance the cursor; when an offset is finished release its index block
+          if (++ct == T) {
+            ct = 0;
+            if (++cc == NCH) {
+              cc = 0;
               __syncwarp();
-              if (lane == 0) mbar_arrive(afull(sig_slot));
-              if (++sig_slot == SA) sig_slot = 0;
+              if (lane == 0) mbar_arrive(iempty(islot));
+              if (++islot == MAX_I) { islot = 0; ++iround; }
+              if (++ck == NSTEP) {
+                ck = 0;
+                ++cg;
+                const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)cg * gridDim.x) * T;
+                tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+              }
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(iempty(islot));
-        if (++islot == MAX_I) { islot = 0; ++iround; }
       }
-    }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      const uint32_t left = issued < (uint32_t)LAG ? issued : (uint32_t)LAG;
-      for (uint32_t q2 = 0; q2 < left; ++q2) {
-        mbar_arrive(afull(sig_slot));
-        if (++sig_slot == SA) sig_slot = 0;
+      // ---- phase 2: store each stage into its A slot as soon as the slot is free ... -------------------------
+      const int slot0 = slot;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        if (d < nb) {
+          mbar_wait(aempty(slot), (round & 1u) ^ 1u);
+          const uint32_t abase = a_base + (uint32_t)slot * A_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) sts128(abase + dst_off[i], v[d][i]);
+          if (++slot == SA) { slot = 0; ++round; }
+        }
       }
+      // ---- ... then ONE proxy fence + warp sync for the whole batch, and one arrival per stage ------------
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        int sl = slot0;
+        for (int d = 0; d < nb; ++d) {
+          mbar_arrive(afull(sl));
+          if (++sl == SA) sl = 0;
+        }
+      }
+      remaining -= nb;
     }
   } else if (warp == WARP_ILOAD) {
-    // ================================ neighbour-index loader (1 thread) =====================
-    if (lane == 0) {
-      int islot = 0;
-      uint32_t iround = 0;
-      const int nsteps = PAIR ? Q : p.K;
-      for (int g = 0; g < my_groups; ++g) {
-        const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
-        const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-        const uint32_t blk = (uint32_t)tvalid * 512u;
-        for (int step = 0; step < nsteps; ++step) {
-          // indices of the group's tvalid*128 consecutive rows for this offset (pair: two offsets)
-          mbar_wait(iempty(islot), (iround & 1u) ^ 1u);
+    // ================================ neighbour-index loader (1 elected lane) ===============
+    int islot = 0;
+    uint32_t iround = 0;
+    for (int g = 0; g < my_groups; ++g) {
+      const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
+      const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
+      const uint32_t blk = (uint32_t)tvalid * 512u;
+      for (int step = 0; step < NSTEP; ++step) {
+        // indices of the group's tvalid*128 consecutive rows for this offset (PAIR: offsets 2*step and 2*step+1)
+        mbar_wait(iempty(islot), (iround & 1u) ^ 1u);
+        if (elect_one()) {
           const uint32_t idst = i_base + (uint32_t)islot * i_bytes;
           if (PAIR) {
-            const int k0 = 2 * step;
-            const bool two = k0 + 1 < p.K;
+            const bool two = 2 * step + 1 < p.K;
             mbar_expect_tx(ifull(islot), two ? 2u * blk : blk);
-            bulk_g2s(idst, p.nbr + (int64_t)k0 * p.n_pad + tile0 * BM, blk, ifull(islot));
-            if (two) bulk_g2s(idst + (uint32_t)T * 512u, p.nbr + (int64_t)(k0 + 1) * p.n_pad + tile0 * BM, blk, ifull(islot));
+            bulk_g2s(idst, p.nbr + (int64_t)(2 * step) * p.n_pad + tile0 * BM, blk, ifull(islot));
+            if (two)
+              bulk_g2s(idst + (uint32_t)T * 512u, p.nbr + (int64_t)(2 * step + 1) * p.n_pad + tile0 * BM, blk, ifull(islot));
           } else {
             mbar_expect_tx(ifull(islot), blk);
             bulk_g2s(idst, p.nbr + (int64_t)step * p.n_pad + tile0 * BM, blk, ifull(islot));
           }
-          if (++islot == MAX_I) { islot = 0; ++iround; }
         }
+        __syncwarp();
+        if (++islot == MAX_I) { islot = 0; ++iround; }
       }
     }
   } else if (warp == WARP_BLOAD) {
-    // ================================ weight-tile loader (1 thread) =========================
-    if (lane == 0) {
-      int bslot = 0;
-      uint32_t bround = 0;
-      for (int g = 0; g < my_groups; ++g) {
-        for (int q = 0; q < Q; ++q) {
-          mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
+    // ================================ weight-tile loader (1 elected lane) ===================
+    int bslot = 0;
+    uint32_t bround = 0;
+    for (int g = 0; g < my_groups; ++g) {
+      for (int q = 0; q < Q; ++q) {
+        mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
+        if (elect_one()) {
           mbar_expect_tx(bfull(bslot), b_bytes);
           bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)q * b_bytes, b_bytes, bfull(bslot));
-          if (++bslot == SB) { bslot = 0; ++bround; }
         }
+        __syncwarp();
+        if (++bslot == SB) { bslot = 0; ++bround; }
       }
     }
   } else if (warp == WARP_MMA) {
-    // ================================ MMA issuer (1 thread) =================================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.n_out);
-      int aslot = 0, bslot = 0;
-      uint32_t around = 0, bround = 0;
-      for (int g = 0; g < my_groups; ++g) {
-        const int buf = g & 1;
-        mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);       // epilogue has drained this TMEM half
-        tc_fence_after();
-        for (int q = 0; q < Q; ++q) {
-          mbar_wait(bfull(bslot), bround & 1u);
-          const uint64_t db = make_desc_sw128(b_base + (uint32_t)bslot * b_bytes);
-          int nk;
-          if (PAIR) nk = 4;
-          else nk = ((q % NCH) == NCH - 1 ? p.last_kc : KC) >> 4;
-          for (int t = 0; t < T; ++t) {
-            mbar_wait(afull(aslot), around & 1u);
-            tc_fence_after();
-            const uint64_t da = make_desc_sw128(a_base + (uint32_t)aslot * A_BYTES);
-            const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
+    // ================================ MMA issuer (warp-uniform loop, 1 elected lane issues) ==
+    const uint32_t idesc = make_idesc(p.n_out);
+    int aslot = 0, bslot = 0;
+    uint32_t around = 0, bround = 0;
+    for (int g = 0; g < my_groups; ++g) {
+      const int buf = g & 1;
+      mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);         // epilogue has drained this TMEM half
+      tc_fence_after();
+      for (int q = 0; q < Q; ++q) {
+        mbar_wait(bfull(bslot), bround & 1u);
+        const uint64_t db = make_desc_sw128(b_base + (uint32_t)bslot * b_bytes);
+        const int nk = PAIR ? 4 : (((q % NCH) == NCH - 1 ? p.last_kc : KC) >> 4);
+        for (int t = 0; t < T; ++t) {
+          mbar_wait(afull(aslot), around & 1u);
+          tc_fence_after();
+          const uint64_t da = make_desc_sw128(a_base + (uint32_t)aslot * A_BYTES);
+          const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
+          if (elect_one()) {
             for (int kk = 0; kk < nk; ++kk)
               umma(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
-            if (++aslot == SA) { aslot = 0; ++around; }
+            umma_commit(aempty(aslot));                                // frees the A slot when these MMAs retire
           }
-          umma_commit(bempty(bslot));
-          if (++bslot == SB) { bslot = 0; ++bround; }
+          __syncwarp();
+          if (++aslot == SA) { aslot = 0; ++around; }
         }
-        umma_commit(accf(buf));                                      // the group's accumulators are complete
+        if (elect_one()) umma_commit(bempty(bslot));
+        __syncwarp();
+        if (++bslot == SB) { bslot = 0; ++bround; }
       }
+      if (elect_one()) umma_commit(accf(buf));                         // the group's accumulators are complete
+      __syncwarp();
     }
-  } else {
+  } else if (warp < EPI_WARPS) {
     // ================================ epilogue (warps 0..3) ==================================
     for (int g = 0; g < my_groups; ++g) {
       const int buf = g & 1;
@@ -464,10 +502,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   }
 }
 
-// Weight image: one tile per stage q = n_out rows of 128 bytes; 16-byte chunk c of row n is stored at
-// chunk position c ^ (n & 7) (the SWIZZLE_128B pattern); unused parts stay zero.
-//   pair  (n_in == 32): q = k/2, chunk = (k&1)*4 + c/8
-//   !pair             : q = k*nch + c/64, chunk = (c%64)/8
+// Weight image: one tile per stage q = k*nch + c/64: n_out rows of 128 bytes; the 16-byte chunk (c%64)/8 of row n
+// is stored at chunk position chunk ^ (n & 7) (the SWIZZLE_128B pattern); unused half rows stay zero.
 __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, int Cout, int transpose, int mirror,
                                   int nch, int pair, __nv_bfloat16* __restrict__ img) {
   const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
@@ -480,16 +516,11 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
   int src_k = (transpose && mirror) ? K - 1 - k : k;
   int ci = transpose ? n : c, co = transpose ? c : n;
   float v = W[((int64_t)src_k * Cin + ci) * Cout + co];
-  int q, chunk;
-  if (pair) { q = k >> 1; chunk = (k & 1) * 4 + (c >> 3); }
-  else { q = k * nch + c / KC; chunk = (c % KC) >> 3; }
+  // pair (n_in == 32): stage q = k/2, chunks 0-3 <- offset 2q, chunks 4-7 <- offset 2q+1
+  const int q = pair ? (k >> 1) : k * nch + c / KC;
+  const int chunk = pair ? (k & 1) * 4 + (c >> 3) : (c % KC) >> 3;
   size_t off = ((size_t)q * n_out + n) * 64 + (size_t)((chunk ^ (n & 7)) << 3) + (c & 7);
   img[off] = __float2bfloat16_rn(v);
-}
-
-static int stages_per_tile(int K, int n_in, bool pair) {
-  if (pair) return (K + 1) / 2;
-  return K * ((n_in + KC - 1) / KC);
 }
 
 }  // namespace tc
@@ -510,9 +541,7 @@ static EncodeTiledFn tc_encoder() {
   }
   return fn;
 }
-// 0: cp.async gather (default), 1: TMA tile::gather4 (SCN_B200_TC_GATHER=tma).  Measured on B200 (profiles/):
-// one gather4 moves only 512 bytes and costs ~77 cycles of issue per SM, i.e. ~6.6 B/clk/SM, against ~16 B/clk/SM
-// for 16-byte cp.async -- so the TMA path, although it zero-fills missing rows for free, is kept as an option only.
+// 0: LDG.128 + STS.128 gather (default), 1: TMA tile::gather4 (SCN_B200_TC_GATHER=tma).
 static int tc_gather_mode() {
   static int v = -1;
   if (v < 0) {
@@ -535,21 +564,21 @@ bool scn_tc_shape_ok(int K, int n_in, int n_out) {
   return K >= 1 && (n_in % 32) == 0 && (n_out % 32) == 0 && n_in >= 32 && n_in <= 256 && n_out >= 32 && n_out <= 256;
 }
 
-// two offsets share a stage only in cp.async mode (the TMA box is one source row wide)
-static bool tc_pair(int n_in) { return n_in == 32 && (tc_gather_mode() == 0 || tc_encoder() == nullptr); }
+// n_in == 32: two offsets share a 64-channel stage (not available with the TMA gather, whose box is one row wide)
+static bool tc_pair(int n_in) { return n_in == 32 && tc_gather_mode() == 0; }
 
 size_t scn_tc_image_bytes(int K, int n_in, int n_out) {
-  return (size_t)tc::stages_per_tile(K, n_in, tc_pair(n_in)) * n_out * 128;
+  const size_t stages = tc_pair(n_in) ? (size_t)(K + 1) / 2 : (size_t)K * ((n_in + tc::KC - 1) / tc::KC);
+  return stages * n_out * 128;
 }
 
 int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s) {
   const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
   const int nch = (n_in + tc::KC - 1) / tc::KC;
-  const int pair = tc_pair(n_in) ? 1 : 0;
   if ((n_in % tc::KC) != 0) SCN_CUDA(cudaMemsetAsync(out, 0, scn_tc_image_bytes(K, n_in, n_out), s));
   int64_t total = (int64_t)K * Cin * Cout;
-  tc::k_prep_weights_tc<<<grid_for(total, 256), 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, nch, pair,
-                                                             (__nv_bfloat16*)out);
+  tc::k_prep_weights_tc<<<grid_for(total, 256), 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, nch,
+                                                             tc_pair(n_in) ? 1 : 0, (__nv_bfloat16*)out);
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }
@@ -575,33 +604,38 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   }
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
-  p.pair = tc_pair(n_in) ? 1 : 0;
-  p.nch = (n_in + tc::KC - 1) / tc::KC;
-  p.last_kc = n_in - (p.nch - 1) * tc::KC;
-  p.Q = tc::stages_per_tile(K, n_in, p.pair != 0);
+  const int nch = (n_in + tc::KC - 1) / tc::KC;
+  p.last_kc = n_in - (nch - 1) * tc::KC;
   p.num_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-  // tiles per group: as many accumulators as fit in half of TMEM, but keep every SM busy
+  // tiles per group: as many accumulators as fit in half of TMEM (weight reuse), chosen to minimise the
+  // number of tiles walked by the busiest CTA
   int tmax = 256 / n_out;
   if (tmax < 1) tmax = 1;
   int T = 1;
   long best = -1;
   for (int cand = tmax; cand >= 1; --cand) {
     long groups = (p.num_tiles + cand - 1) / cand;
-    long busiest = ((groups + kNumSMs - 1) / kNumSMs) * cand;     // tiles walked by the busiest CTA
+    long busiest = ((groups + kNumSMs - 1) / kNumSMs) * cand;
     if (best < 0 || busiest < best) { best = busiest; T = cand; }
   }
   p.T = T;
   p.num_groups = (p.num_tiles + T - 1) / T;
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
-  p.SB = T > 1 ? 3 : 2;
-  if (p.SB > tc::MAX_B) p.SB = tc::MAX_B;
-  const uint32_t i_bytes = (uint32_t)(p.pair ? 2 : 1) * (uint32_t)T * 512u;
+  // bulk copies have ~1-1.5 us latency: keep enough weight tiles in flight to cover it, within ~72 KB
+  {
+    int sb = (int)((48u * 1024u) / b_bytes);
+    if (sb > tc::MAX_B) sb = tc::MAX_B;
+    if (sb < 2) sb = 2;
+    p.SB = sb;
+  }
+  const bool pair = tc_pair(n_in);
+  const uint32_t i_bytes = (uint32_t)(pair ? 2 : 1) * (uint32_t)T * 512u;
   constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 2 * tc::MAX_I + 4;
   const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + (uint32_t)tc::MAX_I * i_bytes + 8u * NBAR + 16u;
   const uint32_t budget = 220u * 1024u;
   int SA = (int)((budget - fixed) / tc::A_BYTES);
   if (SA > tc::MAX_A) SA = tc::MAX_A;
-  if (SA < tc::LAG + 2) return SCN_ERR_UNSUPPORTED;
+  if (SA < tc::D + 1) return SCN_ERR_UNSUPPORTED;
   p.SA = SA;
   size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
   int grid = p.num_groups < kNumSMs ? p.num_groups : kNumSMs;
@@ -611,12 +645,12 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };
-  if (p.pair) return launch(tc::k_conv_tc<true, 1>);
-  switch (p.nch) {
-    case 1: return launch(tc::k_conv_tc<false, 1>);
-    case 2: return launch(tc::k_conv_tc<false, 2>);
-    case 3: return launch(tc::k_conv_tc<false, 3>);
-    case 4: return launch(tc::k_conv_tc<false, 4>);
+  if (pair) return launch(tc::k_conv_tc<1, true>);
+  switch (nch) {
+    case 1: return launch(tc::k_conv_tc<1, false>);
+    case 2: return launch(tc::k_conv_tc<2, false>);
+    case 3: return launch(tc::k_conv_tc<3, false>);
+    case 4: return launch(tc::k_conv_tc<4, false>);
     default: return SCN_ERR_UNSUPPORTED;
   }
 }
