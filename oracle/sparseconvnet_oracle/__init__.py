@@ -31,12 +31,15 @@ __all__ = [
 #   bf16 : bf16 operands AND bf16 feature storage       -> operand_round + storage_round
 # With these flags the oracle does float64 arithmetic on exactly the values the kernels see, so the
 # comparison isolates the kernels' own arithmetic from the precision the mode states.
-NUMERICS = {"operand_round": False, "storage_round": False}
+NUMERICS = {"operand_round": False, "storage_round": False, "fuse": True}
 
 
-def set_numerics(mode: str):
+def set_numerics(mode: str, fuse: bool = True):
+    """fuse: emulate the product's BatchNormalization/AddTable + LeakyReLU fusion, i.e. ONE storage rounding after
+    the activation instead of one after each module (only observable when storage_round is on)."""
     NUMERICS["operand_round"] = mode in ("mixed", "bf16")
     NUMERICS["storage_round"] = mode == "bf16"
+    NUMERICS["fuse"] = fuse
 
 
 def _bf16(t):
@@ -113,10 +116,23 @@ def _sorted(coords):
 
 
 class SparseConvNetTensor:
-    def __init__(self, features=None, metadata=None, spatial_size=None):
-        self.features = features
+    def __init__(self, features=None, metadata=None, spatial_size=None, pending=None):
+        self._features = features
+        self._pending = pending       # (run, fuse) of a BatchNormalization / AddTable awaiting a possible LeakyReLU
         self.metadata = metadata
         self.spatial_size = spatial_size
+
+    @property
+    def features(self):
+        if self._pending is not None:
+            self._features = self._pending[0]()
+            self._pending = None
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._features = value
+        self._pending = None
 
     def get_spatial_locations(self, spatial_size=None):
         sp = tuple(int(v) for v in (self.spatial_size if spatial_size is None else spatial_size))
@@ -219,6 +235,21 @@ class _AddFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         return dout, dout
+
+
+class _AddLeakyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, leak):
+        out = _rs(O.leaky_relu_forward(a + b, leak))
+        ctx.leak = leak
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        d = _rs(O.leaky_relu_backward(out, dout, ctx.leak))
+        return d, d, None
 
 
 class _S2DFn(torch.autograd.Function):
@@ -359,10 +390,17 @@ class BatchNormalization(nn.Module):
             self.weight = self.bias = None
 
     def forward(self, input):
-        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
+        x = input.features
+        assert x.nelement() == 0 or x.size(1) == self.nPlanes
+        training = self.training
+
+        def run(leak=float(self.leakiness)):
+            return _BNFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, training, self.eps,
+                               self.momentum, leak)
+        if NUMERICS["fuse"] and float(self.leakiness) == 1.0:
+            return SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size, pending=(run, run))
         out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
-        out.features = _BNFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
-                                   self.training, self.eps, self.momentum, float(self.leakiness))
+        out.features = run()
         return out
 
 
@@ -383,7 +421,11 @@ class LeakyReLU(nn.Module):
 
     def forward(self, input):
         out = SparseConvNetTensor(metadata=input.metadata, spatial_size=input.spatial_size)
-        out.features = _LeakyFn.apply(input.features, self.leak)
+        pend, input._pending = input._pending, None
+        if pend is not None:
+            out.features = pend[1](float(self.leak))
+        else:
+            out.features = _LeakyFn.apply(input.features, self.leak)
         return out
 
 
@@ -413,6 +455,10 @@ class Identity(nn.Module):
 
 class AddTable(nn.Module):
     def forward(self, input):
+        if NUMERICS["fuse"] and len(input) == 2:
+            a, b = input[0].features, input[1].features
+            return SparseConvNetTensor(metadata=input[0].metadata, spatial_size=input[0].spatial_size,
+                                       pending=(lambda: _AddFn.apply(a, b), lambda leak: _AddLeakyFn.apply(a, b, leak)))
         out = SparseConvNetTensor(metadata=input[0].metadata, spatial_size=input[0].spatial_size)
         feats = input[0].features
         for t in input[1:]:

@@ -116,3 +116,34 @@ __device__ __forceinline__ int hash_lookup_group8(const uint64_t* __restrict__ t
   }
   return result;
 }
+
+// Same lookup with 4 lanes per query: each lane reads two adjacent slots (one 16-byte load), so a query still costs
+// one 64-byte bucket per probe step but only half the threads.  Used by the submanifold rulebook builder.
+__device__ __forceinline__ int hash_lookup_group4(const uint64_t* __restrict__ tk, const int32_t* __restrict__ tv,
+                                                  uint32_t bucket_mask, uint64_t key, bool active) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned sub = lane & 3u;
+  const unsigned gshift = lane & 28u;
+  uint32_t bucket = key_hash(key) & bucket_mask;
+  int result = -1;
+  bool done = !active;
+  while (__any_sync(0xffffffffu, !done)) {
+    ulonglong2 k2 = make_ulonglong2(kEmptyKey, kEmptyKey);
+    if (!done) k2 = *reinterpret_cast<const ulonglong2*>(tk + (size_t)bucket * 8 + sub * 2);
+    const unsigned h0 = (__ballot_sync(0xffffffffu, !done && k2.x == key) >> gshift) & 0xfu;
+    const unsigned h1 = (__ballot_sync(0xffffffffu, !done && k2.y == key) >> gshift) & 0xfu;
+    const unsigned em = (__ballot_sync(0xffffffffu, !done && (k2.x == kEmptyKey || k2.y == kEmptyKey)) >> gshift) & 0xfu;
+    if (!done) {
+      if (h0 | h1) {
+        const int slot = h0 ? (__ffs(h0) - 1) * 2 : (__ffs(h1) - 1) * 2 + 1;
+        result = tv[(size_t)bucket * 8 + slot];
+        done = true;
+      } else if (em) {
+        done = true;
+      } else {
+        bucket = (bucket + 1) & bucket_mask;
+      }
+    }
+  }
+  return result;
+}

@@ -293,8 +293,9 @@ __global__ void __launch_bounds__(128) k_conv_mma(const T* __restrict__ in, cons
 // CTA = 8 warps (2 along n_in x 4 along NT); pairs are compacted from nbr[k][chunk] on the fly,
 // consumed 64 at a time; both operands reach the MMA through ldmatrix.trans.
 // =============================================================================================
-constexpr int kPB = 64;     // pairs per MMA step
-constexpr int kScan = 256;  // rows scanned per compaction step
+constexpr int kPB = 64;        // pairs per MMA step
+constexpr int kScan = 256;     // rows scanned per compaction pass (= threads)
+constexpr int kMaxChunk = 4096;   // rows per CTA: bounds the shared-memory pair list (worst case: every row is a pair)
 
 template <typename T, int MI, int NJ>
 __global__ void __launch_bounds__(256) k_wgrad_mma(const T* __restrict__ in, const T* __restrict__ dout,
@@ -303,12 +304,11 @@ __global__ void __launch_bounds__(256) k_wgrad_mma(const T* __restrict__ in, con
   constexpr int n_in = 32 * MI, NT = 32 * NJ;
   constexpr int lda = n_in + 8, ldb = NT + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [kPB][lda]
-  __nv_bfloat16* sB = sA + kPB * lda;                               // [kPB][ldb]
-  int* s_in = reinterpret_cast<int*>(sB + kPB * ldb);               // [kScan + kPB]
-  int* s_out = s_in + (kScan + kPB);                                // [kScan + kPB]
+  __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem_raw);   // [2][kPB][lda]
+  __nv_bfloat16* sB = sA + 2 * kPB * lda;                           // [2][kPB][ldb]
+  int* s_in = reinterpret_cast<int*>(sB + 2 * kPB * ldb);           // [chunk]
+  int* s_out = s_in + chunk;                                        // [chunk]
   __shared__ int s_warp_cnt[8];
-  __shared__ int s_count;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp & 1, wn = warp >> 1;
@@ -317,81 +317,84 @@ __global__ void __launch_bounds__(256) k_wgrad_mma(const T* __restrict__ in, con
   const int64_t r0 = (int64_t)blockIdx.x * chunk;
   const int64_t r1 = r0 + chunk < n_rows ? r0 + chunk : n_rows;
 
+  // ---- phase A: compact the live (in,out) pairs of offset k in this chunk (order = out row) -----------------
+  int count = 0;
+  for (int64_t rb = r0; rb < r1; rb += kScan) {
+    const int64_t o = rb + tid;
+    int j = -1;
+    if (o < r1) j = nbr[(int64_t)k * n_pad + o];
+    const unsigned m = __ballot_sync(0xffffffffu, j >= 0);
+    if (lane == 0) s_warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int base = count, total = count;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const int c = s_warp_cnt[w];
+      if (w < warp) base += c;
+      total += c;
+    }
+    if (j >= 0) {
+      const int p = base + __popc(m & ((1u << lane) - 1u));
+      s_in[p] = j;
+      s_out[p] = (int)o;
+    }
+    count = total;
+    __syncthreads();
+  }
+  if (count == 0) return;
+
   float acc[MI][NJ][4];
 #pragma unroll
   for (int i = 0; i < MI; ++i)
 #pragma unroll
     for (int j = 0; j < NJ; ++j) acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f;
 
-  if (tid == 0) s_count = 0;
-  __syncthreads();
-
-  for (int64_t rb = r0; rb < r1; rb += kScan) {
-    // ---- scan up to kScan rows, append live pairs --------------------------------------
-    int count = s_count;
-    {
-      int64_t o = rb + tid;
-      int j = -1;
-      if (o < r1) j = nbr[(int64_t)k * n_pad + o];
-      unsigned m = __ballot_sync(0xffffffffu, j >= 0);
-      if (lane == 0) s_warp_cnt[warp] = __popc(m);
-      __syncthreads();
-      int base = count;
-      for (int w = 0; w < warp; ++w) base += s_warp_cnt[w];
-      if (j >= 0) {
-        int p = base + __popc(m & ((1u << lane) - 1u));
-        s_in[p] = j;
-        s_out[p] = (int)o;
-      }
-      int total = count;
-      for (int w = 0; w < 8; ++w) total += s_warp_cnt[w];
-      count = total;
-      __syncthreads();
+  // ---- phase B: double-buffered gather (cp.async) + mma.sync over 64 pairs at a time -------------------------
+  const int nsteps = (count + kPB - 1) / kPB;
+  auto gather = [&](int step, int buf) {
+    const int head = step * kPB;
+    const int take = count - head < kPB ? count - head : kPB;
+    __nv_bfloat16* a = sA + (size_t)buf * kPB * lda;
+    __nv_bfloat16* b = sB + (size_t)buf * kPB * ldb;
+    for (int c = tid; c < kPB * (n_in / 8); c += 256) {
+      const int r = c / (n_in / 8), q = c - r * (n_in / 8);
+      const int64_t row = r < take ? (int64_t)s_in[head + r] : -1;
+      RowChunk<T>::copy(a + r * lda + q * 8, in, row, n_in, q * 8);
     }
-    const bool last = rb + kScan >= r1;
-    // ---- consume kPB pairs at a time -----------------------------------------------------
-    int head = 0;
-    while (count - head >= kPB || (last && count - head > 0)) {
-      const int take = count - head < kPB ? count - head : kPB;
-      for (int c = tid; c < kPB * (n_in / 8); c += 256) {
-        int r = c / (n_in / 8), q = c - r * (n_in / 8);
-        int64_t row = r < take ? (int64_t)s_in[head + r] : -1;
-        RowChunk<T>::copy(sA + r * lda + q * 8, in, row, n_in, q * 8);
-      }
-      for (int c = tid; c < kPB * (NT / 8); c += 256) {
-        int r = c / (NT / 8), q = c - r * (NT / 8);
-        int64_t row = r < take ? (int64_t)s_out[head + r] : -1;
-        RowChunk<T>::copy(sB + r * ldb + q * 8, dout + n0, row, n_out, q * 8);
-      }
-      cp_async_commit();
+    for (int c = tid; c < kPB * (NT / 8); c += 256) {
+      const int r = c / (NT / 8), q = c - r * (NT / 8);
+      const int64_t row = r < take ? (int64_t)s_out[head + r] : -1;
+      RowChunk<T>::copy(b + r * ldb + q * 8, dout + n0, row, n_out, q * 8);
+    }
+    cp_async_commit();
+  };
+  gather(0, 0);
+  for (int s = 0; s < nsteps; ++s) {
+    if (s + 1 < nsteps) {
+      gather(s + 1, (s + 1) & 1);
+      cp_async_wait<1>();
+    } else {
       cp_async_wait<0>();
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < kPB; kk += 16) {
-        uint32_t bf[NJ][2];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-          ldmatrix_x2_trans(smem_u32(sB + (kk + (lane & 15)) * ldb + (wn * NJ + j) * 8), bf[j][0], bf[j][1]);
-#pragma unroll
-        for (int i = 0; i < MI; ++i) {
-          uint32_t a0, a1, a2, a3;
-          const int m0 = (wm * MI + i) * 16;
-          ldmatrix_x4_trans(smem_u32(sA + (kk + (lane >> 4) * 8 + (lane & 7)) * lda + m0 + ((lane >> 3) & 1) * 8), a0,
-                            a1, a2, a3);
-#pragma unroll
-          for (int j = 0; j < NJ; ++j) mma_bf16(acc[i][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
-        }
-      }
-      __syncthreads();
-      head += take;
     }
-    // ---- keep the (< kPB) leftover pairs at the front of the list -----------------------------
-    const int left = count - head;
-    int li = -1, lo = -1;
-    if (tid < left) { li = s_in[head + tid]; lo = s_out[head + tid]; }
     __syncthreads();
-    if (tid < left) { s_in[tid] = li; s_out[tid] = lo; }
-    if (tid == 0) s_count = left;
+    const __nv_bfloat16* a = sA + (size_t)(s & 1) * kPB * lda;
+    const __nv_bfloat16* b = sB + (size_t)(s & 1) * kPB * ldb;
+#pragma unroll
+    for (int kk = 0; kk < kPB; kk += 16) {
+      uint32_t bf[NJ][2];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        ldmatrix_x2_trans(smem_u32(b + (kk + (lane & 15)) * ldb + (wn * NJ + j) * 8), bf[j][0], bf[j][1]);
+#pragma unroll
+      for (int i = 0; i < MI; ++i) {
+        uint32_t a0, a1, a2, a3;
+        const int m0 = (wm * MI + i) * 16;
+        ldmatrix_x4_trans(smem_u32(a + (kk + (lane >> 4) * 8 + (lane & 7)) * lda + m0 + ((lane >> 3) & 1) * 8), a0, a1,
+                          a2, a3);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) mma_bf16(acc[i][j], a0, a1, a2, a3, bf[j][0], bf[j][1]);
+      }
+    }
     __syncthreads();
   }
 
@@ -444,15 +447,14 @@ template <typename T, int MI, int NJ>
 int launch_wgrad_mma(const T* in, const T* dout, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int n_out,
                      float* dW, cudaStream_t s) {
   constexpr int n_in = 32 * MI, NT = 32 * NJ;
-  size_t smem = (size_t)kPB * (n_in + 8 + NT + 8) * sizeof(__nv_bfloat16) + 2 * (kScan + kPB) * sizeof(int);
-  auto kern = k_wgrad_mma<T, MI, NJ>;
-  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int nz = n_out / NT;
   int64_t want = (int64_t)kNumSMs * 8 / ((int64_t)K * nz);
   if (want < 1) want = 1;
-  int64_t max_chunks = (n_rows + kScan - 1) / kScan;
-  if (want > max_chunks) want = max_chunks;
   int64_t chunk = round_up_i64((n_rows + want - 1) / want, kScan);
+  if (chunk > kMaxChunk) chunk = kMaxChunk;
+  size_t smem = (size_t)2 * kPB * (n_in + 8 + NT + 8) * sizeof(__nv_bfloat16) + 2 * (size_t)chunk * sizeof(int);
+  auto kern = k_wgrad_mma<T, MI, NJ>;
+  SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)((n_rows + chunk - 1) / chunk), (unsigned)K, (unsigned)nz);
   kern<<<grid, 256, smem, s>>>(in, dout, nbr, n_rows, n_pad, n_out, (int)chunk, dW);
   SCN_LAUNCH_CHECK();

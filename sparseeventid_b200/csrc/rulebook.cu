@@ -8,14 +8,14 @@
 
 namespace {
 
-// One 8-lane group per (half-offset h, site r).  Probes site + d_h; the mirrored entry
+// One 4-lane group per (half-offset h, site r).  Probes site + d_h; the mirrored entry
 // (K-1-h, neighbour) follows from symmetry, so only (K-1)/2 of the K offsets touch the hash.
 __global__ void k_subm_probe(const uint64_t* __restrict__ keys, int64_t n, const uint64_t* __restrict__ tk,
                              const int32_t* __restrict__ tv, uint32_t bucket_mask, int f0, int f1, int f2, int K,
                              int32_t* __restrict__ nbr, int64_t n_pad) {
   const int half = (K - 1) / 2;
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t item = t >> 3;
+  int64_t item = t >> 2;
   bool active = item < (int64_t)half * n;
   int h = 0;
   int64_t r = 0;
@@ -34,8 +34,8 @@ __global__ void k_subm_probe(const uint64_t* __restrict__ keys, int64_t n, const
     active = ((unsigned)x0 < 65536u) && ((unsigned)x1 < 65536u) && ((unsigned)x2 < 65536u);
     qkey = key_pack(x0, x1, x2, b);
   }
-  int j = hash_lookup_group8(tk, tv, bucket_mask, qkey, active);
-  if (active && (threadIdx.x & 7) == 0 && j >= 0) {
+  int j = hash_lookup_group4(tk, tv, bucket_mask, qkey, active);
+  if (active && (threadIdx.x & 3) == 0 && j >= 0) {
     nbr[(int64_t)h * n_pad + r] = j;
     nbr[(int64_t)(K - 1 - h) * n_pad + j] = (int)r;
   }
@@ -156,7 +156,7 @@ extern "C" int scn_subm_rulebook(const uint64_t* keys, int64_t n, const uint64_t
   k_identity_rows<<<grid_for(n, 256), 256, 0, s>>>(nbr + (int64_t)half * n_pad, n);
   SCN_LAUNCH_CHECK();
   if (half > 0) {
-    k_subm_probe<<<grid_for((int64_t)half * n * 8, 256), 256, 0, s>>>(keys, n, table_keys, table_vals,
+    k_subm_probe<<<grid_for((int64_t)half * n * 4, 256), 256, 0, s>>>(keys, n, table_keys, table_vals,
                                                                       (uint32_t)(capacity / 8 - 1), f0, f1, f2, K, nbr,
                                                                       n_pad);
     SCN_LAUNCH_CHECK();

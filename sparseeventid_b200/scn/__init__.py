@@ -1,5 +1,5 @@
 """B200-native implementation of the ``sparseconvnet`` module surface (see modules.py)."""
-from .config import feature_dtype, get_precision, set_precision
+from .config import feature_dtype, get_precision, set_fusion, set_precision
 from .core import Metadata, SparseConvNetTensor
 from .dense_view import SparseDenseTensor, set_lazy_dense
 from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, Convolution, Deconvolution,
@@ -10,5 +10,5 @@ __all__ = [
     "AddTable", "BatchNormalization", "BatchNormLeakyReLU", "BatchNormReLU", "Convolution", "Deconvolution",
     "Identity", "InputLayer", "LeakyReLU", "OutputLayer", "ReLU", "Sequential", "Sigmoid", "SparseToDense",
     "SubmanifoldConvolution", "Tanh", "SparseConvNetTensor", "Metadata", "set_precision", "get_precision",
-    "feature_dtype", "set_lazy_dense", "SparseDenseTensor",
+    "feature_dtype", "set_lazy_dense", "SparseDenseTensor", "set_fusion",
 ]

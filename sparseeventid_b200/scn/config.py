@@ -15,7 +15,8 @@ import torch
 from .._lib import PREC_BF16, PREC_FP32
 
 _MODES = ("fp32", "mixed", "bf16")
-_state = {"mode": os.environ.get("SCN_B200_PRECISION", "bf16")}
+_state = {"mode": os.environ.get("SCN_B200_PRECISION", "bf16"),
+          "fusion": os.environ.get("SCN_B200_FUSION", "1") not in ("0", "false", "False")}
 if _state["mode"] not in _MODES:
     raise ValueError(f"SCN_B200_PRECISION must be one of {_MODES}")
 
@@ -36,3 +37,12 @@ def feature_dtype() -> torch.dtype:
 
 def precision_code() -> int:
     return PREC_FP32 if _state["mode"] == "fp32" else PREC_BF16
+
+
+def set_fusion(flag: bool) -> None:
+    """Cross-module fusion of BatchNormalization/AddTable with a following LeakyReLU/ReLU (one kernel instead of two)."""
+    _state["fusion"] = bool(flag)
+
+
+def fusion_enabled() -> bool:
+    return _state["fusion"]

@@ -127,13 +127,50 @@ class Metadata:
         return rule
 
 
+class Pending:
+    """A bandwidth-bound layer whose launch is deferred by one module so that the NEXT module can fuse with it:
+    BatchNormalization -> LeakyReLU/ReLU and AddTable -> LeakyReLU/ReLU run as ONE kernel each (forward and
+    backward) instead of two.  Any other consumer reads ``.features``, which runs the deferred layer unfused."""
+
+    __slots__ = ("kind", "run", "fuse")
+
+    def __init__(self, kind, run, fuse):
+        self.kind = kind        # "bn" | "add"
+        self.run = run          # () -> features, the layer as written
+        self.fuse = fuse        # (leak) -> features of layer followed by leaky ReLU
+
+
 class SparseConvNetTensor:
     """features [nActive, C] + shared metadata + spatial_size (LongTensor), as in SCN."""
 
-    def __init__(self, features=None, metadata=None, spatial_size=None):
-        self.features = features
+    def __init__(self, features=None, metadata=None, spatial_size=None, pending=None):
+        self._features = features
+        self._pending = pending
+        self._taken = None
         self.metadata = metadata
         self.spatial_size = spatial_size
+
+    @property
+    def features(self):
+        if self._pending is not None:
+            self._features = self._pending.run()
+            self._pending = None
+        elif self._features is None and self._taken is not None:
+            # a second consumer of a tensor whose layer was fused into a following activation: run it as written
+            self._features = self._taken.run()
+            self._taken = None
+        return self._features
+
+    @features.setter
+    def features(self, value):
+        self._features = value
+        self._pending = None
+
+    def take_pending(self):
+        """Hands the deferred layer to a fusing consumer (the tensor then owns no features of its own)."""
+        pend, self._pending = self._pending, None
+        self._taken = pend
+        return pend
 
     def _sp(self):
         return tuple(int(v) for v in self.spatial_size)

@@ -99,6 +99,25 @@ class AddFn(Function):
         return dout, dout
 
 
+class AddLeakyFn(Function):
+    """out = leaky(a + b): AddTable followed by LeakyReLU in one kernel (reference ResidualBlock tail,
+    src/networks/sparse_building_blocks.py:96-98)."""
+
+    @staticmethod
+    def forward(ctx, a, b, leak):
+        out = ops.add_forward(a.contiguous(), b.contiguous(), leak)
+        ctx.save_for_backward(out)
+        ctx.leak = leak
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (out,) = ctx.saved_tensors
+        # sign(out) == sign(a + b) for leak > 0; for leak == 0 (ReLU) out > 0 <=> a + b > 0 as well
+        d = ops.leaky_backward(out, dout.contiguous(), ctx.leak)
+        return d, d, None
+
+
 class InputLayerFn(Function):
     @staticmethod
     def forward(ctx, feats, rows, n_active, mode):

@@ -14,7 +14,7 @@ from torch import nn
 from .. import _lib as L
 from . import config, dense_view, ops
 from . import functional as F
-from .core import Metadata, SparseConvNetTensor, as_tuple
+from .core import Metadata, Pending, SparseConvNetTensor, as_tuple
 
 
 def _volume(t):
@@ -198,10 +198,17 @@ class BatchNormalization(nn.Module):
             self.register_parameter("bias", None)
 
     def forward(self, input):
-        assert input.features.nelement() == 0 or input.features.size(1) == self.nPlanes
-        feats = F.BatchNormFn.apply(input.features, self.weight, self.bias, self.running_mean, self.running_var,
-                                    self.training, float(self.eps), float(self.momentum), float(self.leakiness))
-        return _new_like(input, feats)
+        x = input.features
+        assert x.nelement() == 0 or x.size(1) == self.nPlanes
+        training = self.training
+
+        def run(leak=float(self.leakiness)):
+            return F.BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, training,
+                                       float(self.eps), float(self.momentum), leak)
+        if config.fusion_enabled() and float(self.leakiness) == 1.0:
+            # defer by one module: a following LeakyReLU/ReLU becomes the fused leakiness of this same kernel
+            return SparseConvNetTensor(None, input.metadata, input.spatial_size, Pending("bn", run, run))
+        return _new_like(input, run())
 
     def __repr__(self):
         return (f"BatchNorm({self.nPlanes},eps={self.eps},momentum={self.momentum},affine={self.affine}"
@@ -226,6 +233,9 @@ class LeakyReLU(nn.Module):
         self.leak = leak
 
     def forward(self, input):
+        pend = input.take_pending() if isinstance(input, SparseConvNetTensor) else None
+        if pend is not None:
+            return _new_like(input, pend.fuse(float(self.leak)))
         return _new_like(input, F.LeakyReLUFn.apply(input.features, float(self.leak)))
 
 
@@ -253,6 +263,15 @@ class AddTable(nn.Module):
     """scn.AddTable(): features = sum of the list's features (rows aligned) -- sparse_building_blocks.py:82,96."""
 
     def forward(self, input):
+        if config.fusion_enabled() and len(input) == 2:
+            a, b = input[0].features, input[1].features
+
+            def run():
+                return F.AddFn.apply(a, b)
+
+            def fuse(leak):
+                return F.AddLeakyFn.apply(a, b, leak)
+            return SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size, Pending("add", run, fuse))
         feats = input[0].features
         for t in input[1:]:
             feats = F.AddFn.apply(feats, t.features)
