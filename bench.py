@@ -289,8 +289,16 @@ def run_ours(args, rank, world, local_rank):
             by = sum(conv_algorithmic(r, eb)[1] for r in tc)
             t = sum(r["ms"] for r in tc) * 1e-3
             peak = peaks["bf16_tflops_sustained"]
-            roof = {"bound": "tensor", "kernel": "gather-GEMM conv fwd/dgrad (k_conv_*)", "achieved": fl / t / 1e12,
-                    "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": None,
+            traffic, traffic_note = None, None
+            prof_path = os.path.join(ROOT, "profiles", "r01_conv_tc_ncu_summary.json")
+            if os.path.exists(prof_path):      # dram bytes of ONE ncu --set full capture of this kernel (committed)
+                pj = json.load(open(prof_path))
+                traffic = pj.get("traffic_bytes_per_launch")
+                traffic_note = ("dram read+write of the captured launch (317485 rows, 64->64, 27 offsets; its algorithmic "
+                                f"bytes: {pj.get('algorithmic_bytes_per_launch')}); `achieved` averages all 216 launches of a step")
+            roof = {"bound": "tensor", "kernel": "gather-GEMM conv fwd/dgrad (k_conv_tc, tcgen05)", "achieved": fl / t / 1e12,
+                    "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "launches": len(tc), "avg_launch_us": t / len(tc) * 1e6,
                     "flops_per_launch": fl / len(tc), "algorithmic_bytes_per_launch": by / len(tc),
                     "achieved_algorithmic_gbs": by / t / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
