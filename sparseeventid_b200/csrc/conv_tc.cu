@@ -5,24 +5,28 @@
 // two groups double-buffered in the 512 columns).  The contraction (K offsets x n_in channels) is cut
 // into stages of 64 channels (one 128-byte shared-memory row).  For every stage q = (offset, chunk):
 //   * the weight tile B(q) (n_out x 128 B, pre-swizzled image) is streamed ONCE per group by a 1-D bulk
-//     async copy (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group; the group's
-//     T*128 neighbour indices arrive the same way into an index ring,
-//   * for each tile, 8 producer warps gather the 128 neighbour rows into a 128B-swizzled K-major A tile:
-//     8 lanes move one 128-byte row (coalesced 16-byte LDG), the loads of D stages are in flight per thread
-//     before the first is stored (STS.128), missing neighbours are written as zeros without a global read,
-//   * 1 thread issues tcgen05.mma (M=128, N=n_out, K=16) accumulating in TMEM,
+//     async copy (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
+//   * for each tile ONE producer warp gathers the stage: it reads the tile's 128 neighbour indices (prefetched one
+//     stage ahead), ballots them, compacts the LIVE rows into a warp-private list and moves only those rows
+//     (8 lanes per 128-byte row, coalesced 16-byte LDG -> STS.128 into the 128B-swizzled K-major A tile, up to
+//     G passes of loads in flight).  The ballots are published as the stage's disable-output-lane mask,
+//   * 1 thread issues tcgen05.mma (M=128, N=n_out, K=16) with that mask: accumulator rows without a neighbour at
+//     this offset are not updated, so their (stale) A rows are never read into a result.  Only the first stage of
+//     a tile, which initialises the accumulator, is written in full (zeros for missing neighbours),
 //   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store while the
 //     next group's MMAs run into the other TMEM half.
 // Every output row is written exactly once: no atomics, deterministic.
 //
-// Measured alternatives for the A gather (profiles/): 16-byte cp.async tops out near
-// 16 B/clk/SM (~950 cycles per 16 KB stage); TMA tile::gather4 (kept as an option, SCN_B200_TC_GATHER=tma)
-// costs ~77 cycles per 512-byte instruction.  LDG.128 + STS.128 is the fastest of the three.
+// Each producer warp owns one A slot (stage n -> warp/slot n mod SA): consecutive uses of a slot's two mbarriers are
+// then consecutive phases, which parity waits require.  SA warps gather SA stages concurrently; a stage costs its
+// warp one L2 round trip, so per-SM gather throughput is SA stages per round trip and moves only live bytes.
+//
+// History (profiles/): dense zero-filled A tiles via 16-byte cp.async (~950 cycles per 16 KB stage),
+// TMA tile::gather4 (~77 cycles per 512-byte instruction) and lock-step LDG/STS batches were measured first; all
+// were bound by moving 128 rows per stage although ~30% are live.
 //
 // Replaces SCN's dConvolution_KMxKN_forwardA/B; reference call sites
 // src/networks/sparse_building_blocks.py:29-34,110-117.
-#include <cuda.h>      // CUtensorMap + enums only; the encoder is fetched with cudaGetDriverEntryPoint (no libcuda link)
-
 #include <cstdlib>
 #include <cstring>
 
@@ -34,15 +38,16 @@ constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int A_BYTES = BM * 128;       // 16 KB
 constexpr int EPI_WARPS = 4;            // warps 0..3  (TMEM lane quarter = warp index)
-constexpr int PROD_WARPS = 8;           // warps 4..11
-constexpr int WARP_MMA = 12;
-constexpr int WARP_BLOAD = 13;          // weight tiles
-constexpr int WARP_ILOAD = 14;          // neighbour-index blocks (separate thread: must never wait on the B ring)
-constexpr int THREADS = 480;
-constexpr int MAX_A = 12, MAX_B = 6, MAX_I = 4;   // ring depths: A tiles, B tiles, neighbour-index blocks
-constexpr int D = 4;                    // stages whose global loads a producer thread keeps in flight
-constexpr int TMA_LANES = 4;            // TMA mode: lanes 0..3 of each producer warp issue one gather4 per stage
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
+constexpr int PROD_WARPS = 11;          // warps 4..14; the first SA of them are active, one per A slot (20 warps in all)
+constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS;   // first of MMA_WARPS issuing warps (tile t -> warp t mod NM)
+constexpr int MMA_WARPS = 4;
+constexpr int WARP_BLOAD = WARP_MMA + MMA_WARPS;   // weight tiles
+constexpr int THREADS = 32 * (WARP_BLOAD + 1);
+constexpr int MAX_A = PROD_WARPS, MAX_B = 6;   // ring depths: A tiles, B tiles
+constexpr int G = 9;                   // gather passes (32 lanes x 16 B each) in flight per warp before the first store
+constexpr int MASK_BYTES = 32;          // per A slot: 2 x 128-bit disable-output-lane masks (second: PAIR upper half)
+constexpr int LIST_BYTES = 128 * 8;     // per producer warp: live items of its stage, (source row, smem address); x2 in PAIR mode
+constexpr uint32_t SPIN_LIMIT = 1u << 20;   // try_wait blocks for a while per call: this is seconds
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -95,6 +100,17 @@ __device__ __forceinline__ bool elect_one() {
       : "=r"(pred));
   return pred != 0;
 }
+// Stage-ready flags: a monotonically increasing sequence number per A slot (release store / acquire poll).  A parity
+// mbarrier cannot be used here: the issuing warps run up to SA stages apart, and a warp waiting for phase k of a slot
+// would be released by phase k-2 when the warp that must consume phase k-1 lags behind.
+__device__ __forceinline__ void st_release_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -106,6 +122,11 @@ __device__ __forceinline__ uint4 ldg_nc128(const void* p) {
                : "l"(p));
   return v;
 }
+__device__ __forceinline__ int ldg_nc32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -114,18 +135,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                : "memory");
-}
-
-// TMA tile::gather4: four rows (arbitrary row coordinates r0..r3, one box of 64 channels starting at column c)
-// of a 2-D tensor land as four consecutive 128-byte rows at dst, swizzled by the tensor map (SWIZZLE_128B);
-// rows/columns outside the tensor are zero-filled without touching memory.  512 bytes complete_tx on `bar`.
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int c, int r0, int r1, int r2, int r3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
-      : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -143,12 +152,15 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+// tcgen05.mma with a disable-output-lane mask: bit r of {m0..m3} set => TMEM lane (= output row) r is NOT updated, so the
+// A-tile row r may hold anything (stale shared memory): rows without a neighbour at this offset are never gathered.
+__device__ __forceinline__ void umma_masked(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate,
+                                            uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -177,16 +189,16 @@ struct Params {
   int K, n_in, n_out;
   int last_kc;                  // channels in the last 64-channel chunk of an offset (64 or 32)
   int T;                        // tiles per group
-  int SA, SB;                   // A / B ring depth
+  int SA, SB;                   // A / B ring depth (SA == number of active producer warps)
   int num_tiles, num_groups;
-  int use_tma;                  // A tiles by TMA gather4 (1) or by LDG+STS (0)
-  int n_in_rows;                // rows of `in` (gather4: any row index >= n_in_rows is zero-filled)
+  int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
+  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 1 no global row loads, 2 no MMAs
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
 // 32 channels each (chunks 0-3 from offset 2q, chunks 4-7 from offset 2q+1), halving the stage count.
 template <int NCH, bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
@@ -195,42 +207,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   const uint32_t b_bytes = (uint32_t)p.n_out * 128u;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)SA * A_BYTES;
-  const uint32_t i_bytes = (uint32_t)(PAIR ? 2 : 1) * (uint32_t)p.T * 512u;   // index block: T tiles x 128 rows (x2 offsets)
-  const uint32_t i_base = b_base + (uint32_t)SB * b_bytes;
-  const uint32_t bar0 = i_base + (uint32_t)MAX_I * i_bytes;  // 8-byte aligned
-  auto afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  const uint32_t bar0 = b_base + (uint32_t)SB * b_bytes;   // 8-byte aligned
   auto aempty = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_A + s); };
   auto bfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + s); };
   auto bempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + MAX_B + s); };
-  auto ifull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + s); };
-  auto iempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + MAX_I + s); };
-  auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + b); };
-  auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 2 + b); };
-  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 2 * MAX_I + 4;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes +
-                                                    (size_t)MAX_I * i_bytes + 8 * NBAR);
-  const int* sidx_all = reinterpret_cast<const int*>(gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes);
+  auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + b); };
+  auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 + b); };
+  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 4;          // 38 -> 304 bytes (a multiple of 16: amask stays 16-byte aligned)
+  unsigned char* tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + 8 * NBAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
+  uint32_t* amask = reinterpret_cast<uint32_t*>(tail + 16);                    // [MAX_A][8], 16-byte aligned
+  unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][LIST_BYTES]
+  const uint32_t aseq = smem_u32(lists + PROD_WARPS * (PAIR ? 2 : 1) * LIST_BYTES);             // [MAX_A] u32: stage number + 1 in slot
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) {
-        // LDG/STS mode: one arrival per producer warp once its rows are stored and fenced;
-        // TMA mode: one arrive.expect_tx(512) per issuing lane, completed by the gather4 bytes
-        mbar_init(afull(s), p.use_tma ? PROD_WARPS * TMA_LANES : PROD_WARPS);
+        st_release_u32(aseq + 4u * (uint32_t)s, 0u);
         mbar_init(aempty(s), 1);                  // one tcgen05.commit
       }
       for (int s = 0; s < SB; ++s) {
         mbar_init(bfull(s), 1);                   // the loader's expect_tx arrival (+ complete_tx bytes)
-        mbar_init(bempty(s), 1);
-      }
-      for (int s = 0; s < MAX_I; ++s) {
-        mbar_init(ifull(s), 1);
-        mbar_init(iempty(s), PROD_WARPS);
+        mbar_init(bempty(s), p.NM);               // one tcgen05.commit per issuing warp
       }
       for (int b = 0; b < 2; ++b) {
-        mbar_init(accf(b), 1);
+        mbar_init(accf(b), p.NM);
         mbar_init(acce(b), EPI_WARPS);
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -245,169 +248,137 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int my_groups = (p.num_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // This CTA's contiguous range of tiles [tile_lo, tile_hi): an even split of the tiles over the grid, cut into groups
+  // of T tiles (only the last group of a CTA can be partial; its missing tiles are not processed by anybody).
   const int T = p.T;
-  const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // index blocks per tile
+  const int tile_lo = (int)(((int64_t)p.num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((int64_t)p.num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int my_tiles = tile_hi - tile_lo;
+  const int my_groups = (my_tiles + T - 1) / T;
+  auto tiles_in_group = [&](int g) { return my_tiles - g * T < T ? my_tiles - g * T : T; };
+  const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // offsets (offset pairs) per tile
   const int Q = NSTEP * NCH;                                // stages per tile
 
-  if (!PAIR && warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS && p.use_tma) {
-    // ================================ A producers, TMA gather4 (option) =====================
-    // lane (pw, l < 4) owns tile rows [16pw + 4l, +4) and moves them with ONE gather4 per stage.  Missing
-    // neighbours (-1) become an out-of-range row index, which the TMA engine zero-fills without reading.
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    // ================================ A producers (warp pw <-> A slot pw) ====================
     const int pw = warp - EPI_WARPS;
-    if (lane < TMA_LANES) {
-      const int r0 = pw * 16 + lane * 4;
-      const uint32_t dst_off = (uint32_t)r0 * 128u;
-      const int oob = p.n_in_rows;
-      int slot = 0, islot = 0;
-      uint32_t round = 0, iround = 0;
-      for (int g = 0; g < my_groups; ++g) {
-        const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
-        const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-        for (int step = 0; step < p.K; ++step) {
-          mbar_wait(ifull(islot), iround & 1u);
-          const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4);
+    if (pw < SA) {
+      // A single warp issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count IS the
+      // gather throughput: the list holds ready-made (source row, swizzled destination address) pairs, one 8-byte
+      // LDS per item, and an item costs ~8 instructions (LDS.64, IMAD.WIDE, LDG.128 / LOP3, STS.128).
+      constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
+      constexpr int IPP = 32 / LPI;                        // items per pass
+      const int chunk = lane % LPI, sub = lane / LPI;
+      int2* list = reinterpret_cast<int2*>(lists + pw * (PAIR ? 2 : 1) * LIST_BYTES);   // .x source row (-1: store zeros), .y smem address
+      const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
+      const int last_chunks = p.last_kc >> 3;
+      const uint32_t lt = (1u << lane) - 1u;
+      const uint32_t abase = a_base + (uint32_t)pw * A_BYTES;
+      const uint32_t csw = (uint32_t)chunk << 4;
+      const int total = my_tiles * Q;                      // stages of this CTA, in MMA order (group, stage, tile)
+      // swizzled address of (row 32i + lane, 16-byte chunk 0) of this warp's slot; upper half (PAIR): chunk 4
+      uint32_t dlo[4];                                     // (upper half: dlo ^ 0x40, the address bits 4-6 hold only the swizzle)
 #pragma unroll
-          for (int chn = 0; chn < NCH; ++chn) {
-            for (int t = 0; t < T; ++t) {
-              int4 jj = make_int4(-1, -1, -1, -1);
-              if (t < tvalid) jj = *reinterpret_cast<const int4*>(sidx + t * 128 + r0);
-              jj.x = jj.x < 0 ? oob : jj.x; jj.y = jj.y < 0 ? oob : jj.y;
-              jj.z = jj.z < 0 ? oob : jj.z; jj.w = jj.w < 0 ? oob : jj.w;
-              mbar_wait(aempty(slot), (round & 1u) ^ 1u);
-              mbar_expect_tx(afull(slot), 512u);
-              tma_gather4(a_base + (uint32_t)slot * A_BYTES + dst_off, &tmap, chn * KC, jj.x, jj.y, jj.z, jj.w, afull(slot));
-              if (++slot == SA) { slot = 0; ++round; }
-            }
-          }
-          // the index block is released by lane 0 of every producer warp (count = PROD_WARPS)
-          __syncwarp(0xFu);
-          if (lane == 0) mbar_arrive(iempty(islot));
-          if (++islot == MAX_I) { islot = 0; ++iround; }
-        }
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t r = 32u * i + lane;
+        dlo[i] = abase + (r << 7) + ((r & 7u) << 4);
       }
-    }
-  } else if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    // ================================ A producers, LDG.128 -> STS.128 ========================
-    // Warp pw owns tile rows [16pw, 16pw+16).  In pass i (0..3) the 8 lanes with the same (lane >> 3) move one
-    // whole 128-byte row: lane handles 16-byte chunk (lane & 7) of row 16pw + 4i + (lane >> 3), so a warp-wide
-    // load touches 4 contiguous 128-byte lines.  Work is done in batches of D stages: first all global loads of
-    // the batch are issued (the neighbour indices come from the shared-memory ring; no waiting on free A slots),
-    // then each stage is stored to its slot as soon as the slot is free, fenced for the async proxy (tensor
-    // core reads) and signalled with ONE mbarrier arrival per warp.
-    const int pw = warp - EPI_WARPS;
-    const int chunk = lane & 7;
-    const int sub = lane >> 3;
-    uint32_t dst_off[4];
-    int rowi[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int rt = pw * 16 + i * 4 + sub;                    // row within the tile
-      rowi[i] = rt;
-      dst_off[i] = (uint32_t)rt * 128u + (((uint32_t)chunk ^ (uint32_t)(rt & 7)) << 4);
-    }
-    const bool hi_half = PAIR && chunk >= 4;                   // this lane's 16 bytes belong to offset 2q+1
-    const uint32_t col_bytes = PAIR ? (uint32_t)(chunk & 3) * 16u : (uint32_t)chunk * 16u;
-    const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
-    const unsigned char* in_bytes = reinterpret_cast<const unsigned char*>(p.in);
-    const int last_chunks = p.last_kc >> 3;
 
-    // issue cursor over (group, offset, chunk, tile)
-    int cg = 0, ck = 0, cc = 0, ct = 0;
-    int tvalid;
-    {
-      const int64_t tile0 = (int64_t)blockIdx.x * T;
-      tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-    }
-    int islot = 0, slot = 0;
-    uint32_t iround = 0, round = 0;
-    int64_t remaining = (int64_t)my_groups * Q * T;
-    while (remaining > 0) {
-      const int nb = remaining < D ? (int)remaining : D;
-      uint4 v[D][4];
-      // ---- phase 1: issue the global loads of up to D stages -------------------------------------------
+      // stage cursor (tile t of stage q of group g), advanced by SA stages at a time
+      int t = 0, q = 0, g = 0;
+      auto advance = [&](int& t_, int& q_, int& g_, int by) {
+        t_ += by;
+        int tv = tiles_in_group(g_);
+        while (t_ >= tv && g_ < my_groups) {
+          t_ -= tv;
+          if (++q_ == Q) { q_ = 0; ++g_; tv = tiles_in_group(g_); }
+        }
+      };
+      advance(t, q, g, pw);
+      // neighbour indices of a stage: lane l holds rows l, 32+l, 64+l, 96+l of the tile (PAIR: of both offsets)
+      auto load_idx = [&](int t_, int q_, int g_, int (&jl)[4], int (&jh)[4]) {
+        const int step = PAIR ? q_ : q_ / NCH;
+        const int64_t tile = (int64_t)tile_lo + (int64_t)g_ * T + t_;
+        const bool ok = true;
+        const int k0 = PAIR ? 2 * step : step;
+        const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + lane;
+        const bool hi_ok = PAIR && ok && (k0 + 1 < p.K);
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (d < nb) {
-          if (cc == 0 && ct == 0) mbar_wait(ifull(islot), iround & 1u);      // first stage of an offset
-          const int* sidx = sidx_all + (size_t)islot * (i_bytes / 4) + ct * 128 + (hi_half ? T * 128 : 0);
-          const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
-          const uint32_t coff = col_bytes + (uint32_t)cc * 128u;
-          const bool tile_ok = ct < tvalid && !(hi_half && 2 * ck + 1 >= p.K);
+        for (int i = 0; i < 4; ++i) {
+          jl[i] = ok ? ldg_nc32(src + 32 * i) : -1;
+          jh[i] = hi_ok ? ldg_nc32(src + p.n_pad + 32 * i) : -1;
+        }
+      };
+
+      int jl[4], jh[4];
+      if (pw < total) load_idx(t, q, g, jl, jh);
+      uint32_t round = 0;
+      for (int n = pw; n < total; n += SA, ++round) {
+        const int cc = PAIR ? 0 : q % NCH;
+        const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
+        // ---- live rows -> list (full stage: every row, missing ones as zeros) --------------------------------
+        uint32_t B[4], H[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          B[i] = __ballot_sync(0xffffffffu, jl[i] >= 0);
+          H[i] = PAIR ? __ballot_sync(0xffffffffu, jh[i] >= 0) : 0u;
+        }
+        int nlive = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int pos = full ? 32 * i + lane : nlive + __popc(B[i] & lt);
+          if (full || jl[i] >= 0) list[pos] = make_int2(jl[i], (int)dlo[i]);
+          nlive += full ? 32 : __popc(B[i]);
+        }
+        if (PAIR) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int j = tile_ok ? sidx[rowi[i]] : -1;
-            v[d][i] = make_uint4(0u, 0u, 0u, 0u);
-            if (j >= 0 && lane_on) v[d][i] = ldg_nc128(in_bytes + ((size_t)(uint32_t)j * row_bytes + coff));
-          }
-          // advance the cursor; when an offset is finished release its index block
-          if (++ct == T) {
-            ct = 0;
-            if (++cc == NCH) {
-              cc = 0;
-              __syncwarp();
-              if (lane == 0) mbar_arrive(iempty(islot));
-              if (++islot == MAX_I) { islot = 0; ++iround; }
-              if (++ck == NSTEP) {
-                ck = 0;
-                ++cg;
-                const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)cg * gridDim.x) * T;
-                tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-              }
-            }
-          }
-        }
-      }
-      // ---- phase 2: store each stage into its A slot as soon as the slot is free ... -------------------------
-      const int slot0 = slot;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (d < nb) {
-          mbar_wait(aempty(slot), (round & 1u) ^ 1u);
-          const uint32_t abase = a_base + (uint32_t)slot * A_BYTES;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) sts128(abase + dst_off[i], v[d][i]);
-          if (++slot == SA) { slot = 0; ++round; }
-        }
-      }
-      // ---- ... then ONE proxy fence + warp sync for the whole batch, and one arrival per stage ------------
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) {
-        int sl = slot0;
-        for (int d = 0; d < nb; ++d) {
-          mbar_arrive(afull(sl));
-          if (++sl == SA) sl = 0;
-        }
-      }
-      remaining -= nb;
-    }
-  } else if (warp == WARP_ILOAD) {
-    // ================================ neighbour-index loader (1 elected lane) ===============
-    int islot = 0;
-    uint32_t iround = 0;
-    for (int g = 0; g < my_groups; ++g) {
-      const int64_t tile0 = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T;
-      const int tvalid = (int)((int64_t)p.num_tiles - tile0 < (int64_t)T ? (int64_t)p.num_tiles - tile0 : (int64_t)T);
-      const uint32_t blk = (uint32_t)tvalid * 512u;
-      for (int step = 0; step < NSTEP; ++step) {
-        // indices of the group's tvalid*128 consecutive rows for this offset (PAIR: offsets 2*step and 2*step+1)
-        mbar_wait(iempty(islot), (iround & 1u) ^ 1u);
-        if (elect_one()) {
-          const uint32_t idst = i_base + (uint32_t)islot * i_bytes;
-          if (PAIR) {
-            const bool two = 2 * step + 1 < p.K;
-            mbar_expect_tx(ifull(islot), two ? 2u * blk : blk);
-            bulk_g2s(idst, p.nbr + (int64_t)(2 * step) * p.n_pad + tile0 * BM, blk, ifull(islot));
-            if (two)
-              bulk_g2s(idst + (uint32_t)T * 512u, p.nbr + (int64_t)(2 * step + 1) * p.n_pad + tile0 * BM, blk, ifull(islot));
-          } else {
-            mbar_expect_tx(ifull(islot), blk);
-            bulk_g2s(idst, p.nbr + (int64_t)step * p.n_pad + tile0 * BM, blk, ifull(islot));
+            const int pos = full ? 128 + 32 * i + lane : nlive + __popc(H[i] & lt);
+            if (full || jh[i] >= 0) list[pos] = make_int2(jh[i], (int)(dlo[i] ^ 0x40u));
+            nlive += full ? 32 : __popc(H[i]);
           }
         }
         __syncwarp();
-        if (++islot == MAX_I) { islot = 0; ++iround; }
+        uint32_t mword = 0;                                // lanes 0..7: the 8 words of the slot's lane masks
+        if (lane < 8) {
+          const uint32_t lo = (lane & 2) ? ((lane & 1) ? B[3] : B[2]) : ((lane & 1) ? B[1] : B[0]);
+          const uint32_t hi = (lane & 2) ? ((lane & 1) ? H[3] : H[2]) : ((lane & 1) ? H[1] : H[0]);
+          mword = ~(lane < 4 ? lo : hi);
+        }
+        // prefetch the next stage's indices (consumed in the next iteration)
+        advance(t, q, g, SA);
+        if (n + SA < total) load_idx(t, q, g, jl, jh);
+
+        const int npass = (nlive + IPP - 1) / IPP;
+        const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
+        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
+        bool first = true;
+        for (int p0 = 0; p0 == 0 || p0 < npass; p0 += G) {
+          int2 e[G];
+          uint4 v[G];
+#pragma unroll
+          for (int gq = 0; gq < G; ++gq) {
+            const int item = (p0 + gq) * IPP + sub;
+            e[gq] = make_int2(-1, 0);
+            if (item < nlive && lane_on) e[gq] = list[item];
+          }
+#pragma unroll
+          for (int gq = 0; gq < G; ++gq) {
+            v[gq] = make_uint4(0u, 0u, 0u, 0u);
+            if (e[gq].x >= 0 && !(p.exp & 1)) v[gq] = ldg_nc128(src0 + (uint64_t)(uint32_t)e[gq].x * row_bytes);
+          }
+          if (first) {
+            first = false;
+            mbar_wait(aempty(pw), (round & 1u) ^ 1u);      // the MMAs that read this slot's previous stage retired
+            if (lane < 8) amask[pw * 8 + lane] = mword;
+          }
+#pragma unroll
+          for (int gq = 0; gq < G; ++gq)
+            if (e[gq].y != 0) sts128((uint32_t)e[gq].y ^ csw, v[gq]);
+        }
+        fence_proxy_async();                               // generic-proxy stores -> async-proxy (tensor core) reads
+        __syncwarp();
+        if (lane == 0) st_release_u32(aseq + 4u * (uint32_t)pw, (uint32_t)n + 1u);   // stage n is ready in slot pw
       }
     }
   } else if (warp == WARP_BLOAD) {
@@ -425,38 +396,69 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
         if (++bslot == SB) { bslot = 0; ++bround; }
       }
     }
-  } else if (warp == WARP_MMA) {
-    // ================================ MMA issuer (warp-uniform loop, 1 elected lane issues) ==
-    const uint32_t idesc = make_idesc(p.n_out);
-    int aslot = 0, bslot = 0;
-    uint32_t around = 0, bround = 0;
-    for (int g = 0; g < my_groups; ++g) {
-      const int buf = g & 1;
-      mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);         // epilogue has drained this TMEM half
-      tc_fence_after();
-      for (int q = 0; q < Q; ++q) {
-        mbar_wait(bfull(bslot), bround & 1u);
-        const uint64_t db = make_desc_sw128(b_base + (uint32_t)bslot * b_bytes);
-        const int nk = PAIR ? 4 : (((q % NCH) == NCH - 1 ? p.last_kc : KC) >> 4);
-        for (int t = 0; t < T; ++t) {
-          mbar_wait(afull(aslot), around & 1u);
-          tc_fence_after();
-          const uint64_t da = make_desc_sw128(a_base + (uint32_t)aslot * A_BYTES);
-          const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
-          if (elect_one()) {
-            for (int kk = 0; kk < nk; ++kk)
-              umma(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u);
-            umma_commit(aempty(aslot));                                // frees the A slot when these MMAs retire
+  } else if (warp >= WARP_MMA && warp < WARP_MMA + MMA_WARPS) {
+    // ================================ MMA issuers (warp-uniform loops, 1 elected lane issues) =
+    // The per-stage issue path (two mbarrier waits, mask fetch, 4 UTCHMMA, commit) costs one warp several hundred
+    // cycles, more than the tensor pipe needs for the stage, so the T tiles of a group (independent accumulators)
+    // are dealt to NM = min(T, 4) issuing warps: warp m issues tiles m, m + NM, ...
+    const int m = warp - WARP_MMA, NM = p.NM;
+    if (m < NM) {
+      const uint32_t idesc = make_idesc(p.n_out);
+      const uint64_t da0 = make_desc_sw128(a_base), db0 = make_desc_sw128(b_base);
+      int bslot = 0;
+      uint32_t bround = 0;
+      for (int g = 0; g < my_groups; ++g) {
+        const int buf = g & 1;
+        const int tv = tiles_in_group(g);
+        const int nbase = g * Q * T;                                  // every earlier group is full
+        mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);       // epilogue has drained this TMEM half
+        tc_fence_after();
+        for (int q = 0; q < Q; ++q) {
+          const int cc = PAIR ? 0 : q % NCH;
+          const int step = PAIR ? q : q / NCH;
+          mbar_wait(bfull(bslot), bround & 1u);
+          const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
+          // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
+          const int nk = (p.exp & 2) ? 0 : (PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4));
+          for (int t = m; t < tv; t += NM) {
+            const int n = nbase + q * tv + t;                          // stage number == producer order
+            const int aslot = n % SA;
+            {
+              uint32_t spins = 0;
+              while (ld_acquire_u32(aseq + 4u * (uint32_t)aslot) != (uint32_t)n + 1u)
+                if (++spins > SPIN_LIMIT) __trap();
+            }
+            __syncwarp();
+            tc_fence_after();
+            // disable-output-lane masks published by the stage's producer: bit r set <=> output row r has no
+            // neighbour at this offset (its A row is stale).  Every lane loads the same words.
+            uint4 mw = make_uint4(0u, 0u, 0u, 0u), hw = make_uint4(0u, 0u, 0u, 0u);
+            if (q > 0) {
+              mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
+              if (PAIR) hw = *reinterpret_cast<const uint4*>(amask + aslot * 8 + 4);
+            }
+            const uint64_t da = da0 + (uint64_t)(((uint32_t)aslot * A_BYTES) >> 4);
+            const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
+            if (elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kk < nk) {
+                  const bool hi = PAIR && kk >= 2;
+                  umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
+                              hi ? hw.x : mw.x, hi ? hw.y : mw.y, hi ? hw.z : mw.z, hi ? hw.w : mw.w);
+                }
+              }
+              umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
+            }
+            __syncwarp();
           }
+          if (elect_one()) umma_commit(bempty(bslot));
           __syncwarp();
-          if (++aslot == SA) { aslot = 0; ++around; }
+          if (++bslot == SB) { bslot = 0; ++bround; }
         }
-        if (elect_one()) umma_commit(bempty(bslot));
+        if (elect_one()) umma_commit(accf(buf));                       // this warp's accumulators of the group are complete
         __syncwarp();
-        if (++bslot == SB) { bslot = 0; ++bround; }
       }
-      if (elect_one()) umma_commit(accf(buf));                         // the group's accumulators are complete
-      __syncwarp();
     }
   } else if (warp < EPI_WARPS) {
     // ================================ epilogue (warps 0..3) ==================================
@@ -464,9 +466,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p, const __
       const int buf = g & 1;
       mbar_wait_sleep(accf(buf), ((uint32_t)g >> 1) & 1u);
       tc_fence_after();
-      for (int t = 0; t < T; ++t) {
-        const int64_t tile = ((int64_t)blockIdx.x + (int64_t)g * gridDim.x) * T + t;
-        if (tile >= p.num_tiles) break;
+      const int tv = tiles_in_group(g);
+      for (int t = 0; t < tv; ++t) {
+        const int64_t tile = (int64_t)tile_lo + (int64_t)g * T + t;
         const int64_t row = tile * BM + warp * 32 + lane;
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
         for (int c0 = 0; c0 < p.n_out; c0 += 32) {
@@ -525,32 +527,6 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
 
 }  // namespace tc
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn tc_encoder() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)f;
-  }
-  return fn;
-}
-// 0: LDG.128 + STS.128 gather (default), 1: TMA tile::gather4 (SCN_B200_TC_GATHER=tma).
-static int tc_gather_mode() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("SCN_B200_TC_GATHER");
-    v = (e && std::strcmp(e, "tma") == 0) ? 1 : 0;
-  }
-  return v;
-}
-
 bool scn_tc_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -564,8 +540,8 @@ bool scn_tc_shape_ok(int K, int n_in, int n_out) {
   return K >= 1 && (n_in % 32) == 0 && (n_out % 32) == 0 && n_in >= 32 && n_in <= 256 && n_out >= 32 && n_out <= 256;
 }
 
-// n_in == 32: two offsets share a 64-channel stage (not available with the TMA gather, whose box is one row wide)
-static bool tc_pair(int n_in) { return n_in == 32 && tc_gather_mode() == 0; }
+// n_in == 32: two offsets share a 64-channel stage
+static bool tc_pair(int n_in) { return n_in == 32; }
 
 size_t scn_tc_image_bytes(int K, int n_in, int n_out) {
   const size_t stages = tc_pair(n_in) ? (size_t)(K + 1) / 2 : (size_t)K * ((n_in + tc::KC - 1) / tc::KC);
@@ -586,62 +562,55 @@ int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mir
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
                    cudaStream_t s) {
+  (void)n_in_rows;
   tc::Params p;
-  CUtensorMap tmap;
-  std::memset(&tmap, 0, sizeof(tmap));
-  p.use_tma = 0;
-  p.n_in_rows = (int)n_in_rows;
-  if (tc_gather_mode() == 1 && tc_encoder() != nullptr && n_in_rows > 0 && n_in_rows < 0x7fffffffLL) {
-    const cuuint64_t gdim[2] = {(cuuint64_t)n_in, (cuuint64_t)n_in_rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)n_in * 2u};
-    const cuuint32_t box[2] = {(cuuint32_t)tc::KC, 1u};
-    const cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = tc_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(in), gdim, gstride,
-                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return SCN_ERR_UNSUPPORTED;
-    p.use_tma = 1;
+  {
+    static int exp_flags = -1;
+    if (exp_flags < 0) {
+      const char* e = std::getenv("SCN_B200_TC_EXP");
+      exp_flags = e ? std::atoi(e) : 0;
+    }
+    p.exp = exp_flags;
   }
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
   const int nch = (n_in + tc::KC - 1) / tc::KC;
   p.last_kc = n_in - (nch - 1) * tc::KC;
   p.num_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-  // tiles per group: as many accumulators as fit in half of TMEM (weight reuse), chosen to minimise the
-  // number of tiles walked by the busiest CTA
-  int tmax = 256 / n_out;
-  if (tmax < 1) tmax = 1;
-  int T = 1;
-  long best = -1;
-  for (int cand = tmax; cand >= 1; --cand) {
-    long groups = (p.num_tiles + cand - 1) / cand;
-    long busiest = ((groups + kNumSMs - 1) / kNumSMs) * cand;
-    if (best < 0 || busiest < best) { best = busiest; T = cand; }
+  // tiles per group: as many accumulators as fit in half of TMEM (weight-tile reuse, and one issuing warp per
+  // tile up to MMA_WARPS); the tiles themselves are split evenly over the CTAs, so T does not unbalance the grid
+  int T = 256 / n_out;
+  if (T < 1) T = 1;
+  if (T > 8) T = 8;
+  {
+    const int per_cta = (p.num_tiles + kNumSMs - 1) / kNumSMs;
+    if (T > per_cta) T = per_cta;
   }
   p.T = T;
-  p.num_groups = (p.num_tiles + T - 1) / T;
+  p.NM = T < tc::MMA_WARPS ? T : tc::MMA_WARPS;
+  p.num_groups = 0;
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
-  // bulk copies have ~1-1.5 us latency: keep enough weight tiles in flight to cover it, within ~72 KB
+  // bulk copies have ~1-1.5 us latency: keep a few weight tiles in flight to cover it, within ~32 KB
   {
-    int sb = (int)((48u * 1024u) / b_bytes);
+    int sb = (int)((32u * 1024u) / b_bytes);
     if (sb > tc::MAX_B) sb = tc::MAX_B;
     if (sb < 2) sb = 2;
     p.SB = sb;
   }
   const bool pair = tc_pair(n_in);
-  const uint32_t i_bytes = (uint32_t)(pair ? 2 : 1) * (uint32_t)T * 512u;
-  constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 2 * tc::MAX_I + 4;
-  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + (uint32_t)tc::MAX_I * i_bytes + 8u * NBAR + 16u;
-  const uint32_t budget = 220u * 1024u;
+  constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 4;
+  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + 8u * NBAR + 16u + (uint32_t)tc::MAX_A * tc::MASK_BYTES +
+                         (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES * (pair ? 2u : 1u) + 4u * tc::MAX_A + 12u;
+  const uint32_t budget = 226u * 1024u;
   int SA = (int)((budget - fixed) / tc::A_BYTES);
-  if (SA > tc::MAX_A) SA = tc::MAX_A;
-  if (SA < tc::D + 1) return SCN_ERR_UNSUPPORTED;
+  if (SA > tc::MAX_A) SA = tc::MAX_A;            // one producer warp per A slot
+  if (SA < 4) return SCN_ERR_UNSUPPORTED;
   p.SA = SA;
   size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
-  int grid = p.num_groups < kNumSMs ? p.num_groups : kNumSMs;
+  int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   auto launch = [&](auto kern) -> int {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tc::THREADS, smem, s>>>(p, tmap);
+    kern<<<grid, tc::THREADS, smem, s>>>(p);
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };
