@@ -18,7 +18,7 @@ LIB = os.path.join(LIB_DIR, "libscn_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations",
-         "--expt-relaxed-constexpr"]
+         "--expt-relaxed-constexpr"] + os.environ.get("SCN_B200_NVCC_FLAGS", "").split()   # e.g. -DSCN_TC_TIMELINE
 
 
 def _sources():

@@ -38,13 +38,12 @@ constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int A_BYTES = BM * 128;       // 16 KB
 constexpr int EPI_WARPS = 4;            // warps 0..3  (TMEM lane quarter = warp index)
-constexpr int PROD_WARPS = 11;          // warps 4..14; the first SA of them are active, one per A slot (20 warps in all)
+constexpr int PROD_WARPS = 6;           // warps 4..9; the first SA/2 of them are active, two A slots each
 constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS;   // first of MMA_WARPS issuing warps (tile t -> warp t mod NM)
 constexpr int MMA_WARPS = 4;
 constexpr int WARP_BLOAD = WARP_MMA + MMA_WARPS;   // weight tiles
 constexpr int THREADS = 32 * (WARP_BLOAD + 1);
-constexpr int MAX_A = PROD_WARPS, MAX_B = 6;   // ring depths: A tiles, B tiles
-constexpr int G = 9;                   // gather passes (32 lanes x 16 B each) in flight per warp before the first store
+constexpr int MAX_A = 2 * PROD_WARPS, MAX_B = 6;   // ring depths: A tiles, B tiles
 constexpr int MASK_BYTES = 32;          // per A slot: 2 x 128-bit disable-output-lane masks (second: PAIR upper half)
 constexpr int LIST_BYTES = 128 * 8;     // per producer warp: live items of its stage, (source row, smem address); x2 in PAIR mode
 constexpr uint32_t SPIN_LIMIT = 1u << 20;   // try_wait blocks for a while per call: this is seconds
@@ -65,6 +64,18 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe (try_wait may suspend the thread for a while; test_wait never does)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(bar), "r"(parity)
@@ -126,6 +137,18 @@ __device__ __forceinline__ int ldg_nc32(const int* p) {
   int v;
   asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+}
+// 16-byte asynchronous global->shared copy (LDGSTS, L2 only); src_bytes == 0 writes zeros without reading
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// this thread's arrival on `bar` fires when all its cp.async issued so far have landed (the count is pre-charged at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
@@ -192,7 +215,9 @@ struct Params {
   int SA, SB;                   // A / B ring depth (SA == number of active producer warps)
   int num_tiles, num_groups;
   int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
-  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 1 no global row loads, 2 no MMAs
+  int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
+  unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
+  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 1 no row loads, 2 no MMAs, 8 no weight loads
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)SA * A_BYTES;
   const uint32_t bar0 = b_base + (uint32_t)SB * b_bytes;   // 8-byte aligned
+  auto afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
   auto aempty = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_A + s); };
   auto bfull = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + s); };
   auto bempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + MAX_B + s); };
@@ -221,11 +247,22 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   const uint32_t aseq = smem_u32(lists + PROD_WARPS * (PAIR ? 2 : 1) * LIST_BYTES);             // [MAX_A] u32: stage number + 1 in slot
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // timeline marks: dbg[((role * 256 + stage) * 8 + event)] = clock64(), CTA 0 only, first 256 stages
+  // (compiled in only with -DSCN_TC_TIMELINE: the marks cost the single-warp issue loops real time)
+  auto mark = [&](int role, int stage, int ev) {
+#ifdef SCN_TC_TIMELINE
+    if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && stage < 256)
+      p.dbg[((size_t)role * 256 + stage) * 8 + ev] = (unsigned long long)clock64();
+#else
+    (void)role; (void)stage; (void)ev;
+#endif
+  };
 
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) {
         st_release_u32(aseq + 4u * (uint32_t)s, 0u);
+        mbar_init(afull(s), 32);                  // the 32 lanes of the owning producer warp, each when its copies landed
         mbar_init(aempty(s), 1);                  // one tcgen05.commit
       }
       for (int s = 0; s < SB; ++s) {
@@ -261,30 +298,34 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // ================================ A producers (warp pw <-> A slot pw) ====================
+    // NPW = SA/2 warps are active; warp pw owns A slots pw and pw + NPW and alternates between them (stage n -> warp
+    // n mod NPW, slot n mod SA), so a slot has one producer and its mbarrier sees consecutive phases (parity-safe).
+    // A single warp issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count IS the
+    // gather throughput: the list holds ready-made (source row, swizzled destination address) pairs, and an item
+    // costs one LDS.64, one IMAD.WIDE, one LOP3 and one 16-byte LDGSTS per lane.  The copies are asynchronous: the
+    // warp builds and issues its next stage (other slot) while this one is in flight, then waits, fences and publishes.
     const int pw = warp - EPI_WARPS;
-    if (pw < SA) {
-      // A single warp issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count IS the
-      // gather throughput: the list holds ready-made (source row, swizzled destination address) pairs, one 8-byte
-      // LDS per item, and an item costs ~8 instructions (LDS.64, IMAD.WIDE, LDG.128 / LOP3, STS.128).
+    const int NPW = SA >> 1;
+    if (pw < NPW) {
       constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
       constexpr int IPP = 32 / LPI;                        // items per pass
       const int chunk = lane % LPI, sub = lane / LPI;
-      int2* list = reinterpret_cast<int2*>(lists + pw * (PAIR ? 2 : 1) * LIST_BYTES);   // .x source row (-1: store zeros), .y smem address
-      const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
+      int2* list = reinterpret_cast<int2*>(lists + pw * (PAIR ? 2 : 1) * LIST_BYTES);   // .x source row offset / 16 B (-1: zeros), .y smem address
+      const uint32_t row_vec = (uint32_t)p.n_in >> 3;      // 16-byte units per feature row (list offsets are in these units)
       const int last_chunks = p.last_kc >> 3;
       const uint32_t lt = (1u << lane) - 1u;
-      const uint32_t abase = a_base + (uint32_t)pw * A_BYTES;
       const uint32_t csw = (uint32_t)chunk << 4;
+      const uint32_t slot_stride = (uint32_t)NPW * A_BYTES;
       const int total = my_tiles * Q;                      // stages of this CTA, in MMA order (group, stage, tile)
-      // swizzled address of (row 32i + lane, 16-byte chunk 0) of this warp's slot; upper half (PAIR): chunk 4
-      uint32_t dlo[4];                                     // (upper half: dlo ^ 0x40, the address bits 4-6 hold only the swizzle)
+      // swizzled address of (row 32i + lane, 16-byte chunk 0) in slot pw (upper half, PAIR: ^ 0x40; other slot: + stride)
+      uint32_t dlo[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const uint32_t r = 32u * i + lane;
-        dlo[i] = abase + (r << 7) + ((r & 7u) << 4);
+        dlo[i] = a_base + (uint32_t)pw * A_BYTES + (r << 7) + ((r & 7u) << 4);
       }
 
-      // stage cursor (tile t of stage q of group g), advanced by SA stages at a time
+      // stage cursor (tile t of stage q of group g)
       int t = 0, q = 0, g = 0;
       auto advance = [&](int& t_, int& q_, int& g_, int by) {
         t_ += by;
@@ -299,21 +340,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       auto load_idx = [&](int t_, int q_, int g_, int (&jl)[4], int (&jh)[4]) {
         const int step = PAIR ? q_ : q_ / NCH;
         const int64_t tile = (int64_t)tile_lo + (int64_t)g_ * T + t_;
-        const bool ok = true;
         const int k0 = PAIR ? 2 * step : step;
         const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + lane;
-        const bool hi_ok = PAIR && ok && (k0 + 1 < p.K);
+        const bool hi_ok = PAIR && (k0 + 1 < p.K);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          jl[i] = ok ? ldg_nc32(src + 32 * i) : -1;
+          jl[i] = ldg_nc32(src + 32 * i);
           jh[i] = hi_ok ? ldg_nc32(src + p.n_pad + 32 * i) : -1;
         }
       };
 
       int jl[4], jh[4];
       if (pw < total) load_idx(t, q, g, jl, jh);
-      uint32_t round = 0;
-      for (int n = pw; n < total; n += SA, ++round) {
+      int it = 0;
+      for (int n = pw; n < total; n += NPW, ++it) {
+        const int slot = pw + (it & 1) * NPW;
+        const uint32_t soff = (it & 1) ? slot_stride : 0u;
+        mark(0, n, 0);
         const int cc = PAIR ? 0 : q % NCH;
         const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
         // ---- live rows -> list (full stage: every row, missing ones as zeros) --------------------------------
@@ -327,14 +370,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int pos = full ? 32 * i + lane : nlive + __popc(B[i] & lt);
-          if (full || jl[i] >= 0) list[pos] = make_int2(jl[i], (int)dlo[i]);
+          if (full || jl[i] >= 0) list[pos] = make_int2(jl[i] >= 0 ? (int)((uint32_t)jl[i] * row_vec) : -1, (int)(dlo[i] + soff));
           nlive += full ? 32 : __popc(B[i]);
         }
         if (PAIR) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int pos = full ? 128 + 32 * i + lane : nlive + __popc(H[i] & lt);
-            if (full || jh[i] >= 0) list[pos] = make_int2(jh[i], (int)(dlo[i] ^ 0x40u));
+            if (full || jh[i] >= 0) list[pos] = make_int2(jh[i] >= 0 ? (int)((uint32_t)jh[i] * row_vec) : -1, (int)((dlo[i] + soff) ^ 0x40u));
             nlive += full ? 32 : __popc(H[i]);
           }
         }
@@ -345,56 +388,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
           const uint32_t hi = (lane & 2) ? ((lane & 1) ? H[3] : H[2]) : ((lane & 1) ? H[1] : H[0]);
           mword = ~(lane < 4 ? lo : hi);
         }
+        mark(0, n, 1);
         // prefetch the next stage's indices (consumed in the next iteration)
-        advance(t, q, g, SA);
-        if (n + SA < total) load_idx(t, q, g, jl, jh);
+        advance(t, q, g, NPW);
+        if (n + NPW < total) load_idx(t, q, g, jl, jh);
 
+        // the MMAs that read this slot's previous stage (two iterations ago) have retired
+        mbar_wait(aempty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);
+        if (lane < 8) amask[slot * 8 + lane] = mword;
+        mark(0, n, 2);
         const int npass = (nlive + IPP - 1) / IPP;
         const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
-        bool first = true;
-        for (int p0 = 0; p0 == 0 || p0 < npass; p0 += G) {
-          int2 e[G];
-          uint4 v[G];
+        if (lane_on) {
+          for (int p0 = 0; p0 < npass; p0 += 6) {          // 6 list entries are read before their copies are issued
+            int2 e[6];
 #pragma unroll
-          for (int gq = 0; gq < G; ++gq) {
-            const int item = (p0 + gq) * IPP + sub;
-            e[gq] = make_int2(-1, 0);
-            if (item < nlive && lane_on) e[gq] = list[item];
-          }
+            for (int u = 0; u < 6; ++u) {
+              const int item = (p0 + u) * IPP + sub;
+              e[u] = make_int2(-1, 0);
+              if (item < nlive) e[u] = list[item];
+            }
 #pragma unroll
-          for (int gq = 0; gq < G; ++gq) {
-            v[gq] = make_uint4(0u, 0u, 0u, 0u);
-            if (e[gq].x >= 0 && !(p.exp & 1)) v[gq] = ldg_nc128(src0 + (uint64_t)(uint32_t)e[gq].x * row_bytes);
+            for (int u = 0; u < 6; ++u) {
+              if (e[u].y != 0) {
+                const bool live = e[u].x != -1 && !(p.exp & 1);     // .x: offset of the source row in 16-byte units, -1: zeros
+                cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e[u].x : 0u) << 4), live ? 16u : 0u);
+              }
+            }
           }
-          if (first) {
-            first = false;
-            mbar_wait(aempty(pw), (round & 1u) ^ 1u);      // the MMAs that read this slot's previous stage retired
-            if (lane < 8) amask[pw * 8 + lane] = mword;
-          }
-#pragma unroll
-          for (int gq = 0; gq < G; ++gq)
-            if (e[gq].y != 0) sts128((uint32_t)e[gq].y ^ csw, v[gq]);
         }
-        fence_proxy_async();                               // generic-proxy stores -> async-proxy (tensor core) reads
-        __syncwarp();
-        if (lane == 0) st_release_u32(aseq + 4u * (uint32_t)pw, (uint32_t)n + 1u);   // stage n is ready in slot pw
+        // Landing is signalled by the copies themselves: every lane's arrival on afull(slot) fires when its cp.async
+        // have completed.  The sequence flag only tells the issuing warps WHICH stage the slot now holds (and the
+        // parity of the landing phase to wait for); the producer never waits for its own copies.
+        cp_async_arrive_noinc(afull(slot));
+        __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
+        if (lane == 0)
+          st_release_u32(aseq + 4u * (uint32_t)slot, ((uint32_t)n + 1u) | ((((uint32_t)it >> 1) & 1u) << 31));
+        mark(0, n, 3);
       }
     }
   } else if (warp == WARP_BLOAD) {
-    // ================================ weight-tile loader (1 elected lane) ===================
+    // ================================ weight-tile loader (1 elected lane, bulk async copies) ==
+    // The tiles (n_out x 128 B each, already in the swizzled shared-memory image) stream from L2 in stage order; the
+    // copy engine signals bfull itself (complete_tx), so landing needs no warp and no proxy fence.
+    const int total_b = my_groups * Q;
     int bslot = 0;
     uint32_t bround = 0;
-    for (int g = 0; g < my_groups; ++g) {
-      for (int q = 0; q < Q; ++q) {
-        mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
-        if (elect_one()) {
-          mbar_expect_tx(bfull(bslot), b_bytes);
-          bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)q * b_bytes, b_bytes, bfull(bslot));
-        }
-        __syncwarp();
-        if (++bslot == SB) { bslot = 0; ++bround; }
+    for (int i = 0; i < total_b; ++i) {
+      mark(2, i, 0);
+      mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
+      mark(2, i, 1);
+      if (elect_one()) {
+        mbar_expect_tx(bfull(bslot), b_bytes);
+        bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)(i % Q) * b_bytes, b_bytes, bfull(bslot));
       }
+      __syncwarp();
+      if (++bslot == SB) { bslot = 0; ++bround; }
     }
   } else if (warp >= WARP_MMA && warp < WARP_MMA + MMA_WARPS) {
     // ================================ MMA issuers (warp-uniform loops, 1 elected lane issues) =
@@ -405,39 +455,57 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     if (m < NM) {
       const uint32_t idesc = make_idesc(p.n_out);
       const uint64_t da0 = make_desc_sw128(a_base), db0 = make_desc_sw128(b_base);
+      const int nbuf = p.nbuf;
       int bslot = 0;
       uint32_t bround = 0;
+      int aslot = m % SA;                                             // slot of this warp's next stage (n mod SA), kept incrementally
+      uint32_t seq = (uint32_t)m + 1u;                                // its sequence number (n + 1)
       for (int g = 0; g < my_groups; ++g) {
-        const int buf = g & 1;
+        const int buf = nbuf == 2 ? (g & 1) : 0;
+        const uint32_t use = (uint32_t)(nbuf == 2 ? (g >> 1) : g);    // how many times this buffer has been used before
         const int tv = tiles_in_group(g);
-        const int nbase = g * Q * T;                                  // every earlier group is full
-        mbar_wait(acce(buf), (((uint32_t)g >> 1) & 1u) ^ 1u);       // epilogue has drained this TMEM half
+        mbar_wait(acce(buf), (use & 1u) ^ 1u);                        // epilogue has drained this accumulator buffer
         tc_fence_after();
         for (int q = 0; q < Q; ++q) {
           const int cc = PAIR ? 0 : q % NCH;
           const int step = PAIR ? q : q / NCH;
+          mark(3, g * Q + q, 0);
           mbar_wait(bfull(bslot), bround & 1u);
+          mark(3, g * Q + q, 1);
           const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
           // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
           const int nk = (p.exp & 2) ? 0 : (PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4));
-          for (int t = m; t < tv; t += NM) {
-            const int n = nbase + q * tv + t;                          // stage number == producer order
-            const int aslot = n % SA;
+          int t = m;
+          for (; t < tv; t += NM) {
+            mark(1, (int)seq - 1, 0);
             {
-              uint32_t spins = 0;
-              while (ld_acquire_u32(aseq + 4u * (uint32_t)aslot) != (uint32_t)n + 1u)
+              uint32_t spins = 0, f;
+              while (((f = ld_acquire_u32(aseq + 4u * (uint32_t)aslot)) & 0x7fffffffu) != seq)   // slot holds stage n?
                 if (++spins > SPIN_LIMIT) __trap();
+              __syncwarp();
+              mbar_wait(afull(aslot), f >> 31);              // ... and its rows have landed (phase parity from the flag)
             }
-            __syncwarp();
+            mark(1, (int)seq - 1, 1);
             tc_fence_after();
             // disable-output-lane masks published by the stage's producer: bit r set <=> output row r has no
-            // neighbour at this offset (its A row is stale).  Every lane loads the same words.
-            uint4 mw = make_uint4(0u, 0u, 0u, 0u), hw = make_uint4(0u, 0u, 0u, 0u);
+            // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
+            // them provably warp-uniform so they are moved to uniform registers once.
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
             if (q > 0) {
-              mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
-              if (PAIR) hw = *reinterpret_cast<const uint4*>(amask + aslot * 8 + 4);
+              const uint4 mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
+              m0 = __ballot_sync(0xffffffffu, (mw.x >> lane) & 1u);
+              m1 = __ballot_sync(0xffffffffu, (mw.y >> lane) & 1u);
+              m2 = __ballot_sync(0xffffffffu, (mw.z >> lane) & 1u);
+              m3 = __ballot_sync(0xffffffffu, (mw.w >> lane) & 1u);
+              if (PAIR) {
+                const uint4 hw = *reinterpret_cast<const uint4*>(amask + aslot * 8 + 4);
+                h0 = __ballot_sync(0xffffffffu, (hw.x >> lane) & 1u);
+                h1 = __ballot_sync(0xffffffffu, (hw.y >> lane) & 1u);
+                h2 = __ballot_sync(0xffffffffu, (hw.z >> lane) & 1u);
+                h3 = __ballot_sync(0xffffffffu, (hw.w >> lane) & 1u);
+              }
             }
-            const uint64_t da = da0 + (uint64_t)(((uint32_t)aslot * A_BYTES) >> 4);
+            const uint64_t da = da0 + (uint64_t)((uint32_t)aslot * (A_BYTES >> 4));
             const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
             if (elect_one()) {
 #pragma unroll
@@ -445,12 +513,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
                 if (kk < nk) {
                   const bool hi = PAIR && kk >= 2;
                   umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
-                              hi ? hw.x : mw.x, hi ? hw.y : mw.y, hi ? hw.z : mw.z, hi ? hw.w : mw.w);
+                              hi ? h0 : m0, hi ? h1 : m1, hi ? h2 : m2, hi ? h3 : m3);
                 }
               }
               umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
             }
             __syncwarp();
+            mark(1, (int)seq - 1, 2);
+            aslot += NM; if (aslot >= SA) aslot -= SA;                 // NM <= 4 <= SA
+            seq += (uint32_t)NM;
+          }
+          // this warp's next stage is tile m of the next q (or group): skip the tiles of other warps in between
+          {
+            const int adv = tv - t + m;                                // stages from (q, t) to (q + 1, m): tv - t + m, may be negative
+            int a2 = aslot + adv;
+            while (a2 < 0) a2 += SA;
+            while (a2 >= SA) a2 -= SA;
+            aslot = a2;
+            seq = (uint32_t)((int)seq + adv);
           }
           if (elect_one()) umma_commit(bempty(bslot));
           __syncwarp();
@@ -463,8 +543,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   } else if (warp < EPI_WARPS) {
     // ================================ epilogue (warps 0..3) ==================================
     for (int g = 0; g < my_groups; ++g) {
-      const int buf = g & 1;
-      mbar_wait_sleep(accf(buf), ((uint32_t)g >> 1) & 1u);
+      const int buf = p.nbuf == 2 ? (g & 1) : 0;
+      mbar_wait_sleep(accf(buf), (uint32_t)(p.nbuf == 2 ? (g >> 1) : g) & 1u);
       tc_fence_after();
       const int tv = tiles_in_group(g);
       for (int t = 0; t < tv; ++t) {
@@ -527,6 +607,10 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
 
 }  // namespace tc
 
+// Debug: device buffer of 4 roles x 256 stages x 8 marks (uint64) filled by CTA 0 of the following launches; NULL disables.
+static unsigned long long* g_tc_dbg = nullptr;
+extern "C" void scn_tc_debug_timeline(void* device_buffer) { g_tc_dbg = (unsigned long long*)device_buffer; }
+
 bool scn_tc_disabled() {
   static int v = -1;
   if (v < 0) {
@@ -562,7 +646,7 @@ int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mir
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
                    cudaStream_t s) {
-  (void)n_in_rows;
+  if ((uint64_t)n_in_rows * (uint64_t)(n_in >> 3) >= 0xffffffffull) return SCN_ERR_UNSUPPORTED;   // 32-bit offsets in 16-byte units (64 GB)
   tc::Params p;
   {
     static int exp_flags = -1;
@@ -572,6 +656,7 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
     }
     p.exp = exp_flags;
   }
+  p.dbg = g_tc_dbg;
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
   const int nch = (n_in + tc::KC - 1) / tc::KC;
@@ -582,17 +667,24 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   int T = 256 / n_out;
   if (T < 1) T = 1;
   if (T > 8) T = 8;
+  p.nbuf = 2;
+  const int per_cta = (p.num_tiles + kNumSMs - 1) / kNumSMs;
   {
-    const int per_cta = (p.num_tiles + kNumSMs - 1) / kNumSMs;
-    if (T > per_cta) T = per_cta;
+    // One group in all 512 TMEM columns instead of two alternating halves: the epilogue then no longer overlaps the
+    // next group's MMAs, but T doubles (more issuing warps, more weight-tile reuse).  Worth it when a CTA has a
+    // single group anyway, or when half of TMEM holds one tile only.
+    int t1 = 512 / n_out;
+    if (t1 > 8) t1 = 8;
+    if (t1 > T && (per_cta <= t1 || T == 1)) { T = t1; p.nbuf = 1; }
   }
+  if (T > per_cta) T = per_cta;
   p.T = T;
   p.NM = T < tc::MMA_WARPS ? T : tc::MMA_WARPS;
   p.num_groups = 0;
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
-  // bulk copies have ~1-1.5 us latency: keep a few weight tiles in flight to cover it, within ~32 KB
+  // weight ring: up to 4 tiles (3 in flight behind the one being consumed), within ~72 KB
   {
-    int sb = (int)((32u * 1024u) / b_bytes);
+    int sb = (int)((72u * 1024u) / b_bytes);
     if (sb > tc::MAX_B) sb = tc::MAX_B;
     if (sb < 2) sb = 2;
     p.SB = sb;
@@ -603,7 +695,8 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
                          (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES * (pair ? 2u : 1u) + 4u * tc::MAX_A + 12u;
   const uint32_t budget = 226u * 1024u;
   int SA = (int)((budget - fixed) / tc::A_BYTES);
-  if (SA > tc::MAX_A) SA = tc::MAX_A;            // one producer warp per A slot
+  if (SA > tc::MAX_A) SA = tc::MAX_A;
+  SA &= ~1;                                      // two A slots per producer warp
   if (SA < 4) return SCN_ERR_UNSUPPORTED;
   p.SA = SA;
   size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;

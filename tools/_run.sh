@@ -1,2 +1,4 @@
-timeout 200 ncu --set full --import-source on --clock-control none -k regex:k_conv_tc -s 2 -c 1 -o gpurun_out/tc_new2 -f python tools/tc_profile.py 317485 27 64 64 3 > gpurun_out/ncu_new.log 2>&1
-tail -2 gpurun_out/ncu_new.log
+python tools/tc_timeline.py 150000 27 96 96 > gpurun_out/tl_96.txt 2>&1
+python tools/tc_timeline.py 500000 27 32 32 > gpurun_out/tl_32.txt 2>&1
+python tools/tc_timeline.py 317485 27 64 64 > gpurun_out/tl_64.txt 2>&1
+tail -n 2 gpurun_out/tl_96.txt gpurun_out/tl_32.txt gpurun_out/tl_64.txt
