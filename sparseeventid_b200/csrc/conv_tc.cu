@@ -217,7 +217,7 @@ struct Params {
   int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
   int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
   unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
-  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 1 no row loads, 2 no MMAs, 8 no weight loads
+  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 2 no MMAs
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][LIST_BYTES]
   const uint32_t aseq = smem_u32(lists + PROD_WARPS * (PAIR ? 2 : 1) * LIST_BYTES);             // [MAX_A] u32: stage number + 1 in slot
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a broadcast shuffle: the compiler then knows it is warp-uniform (role branches, barrier
+  // addresses and slot numbers stay in uniform registers instead of per-lane copies with R2UR waterfalls)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   // timeline marks: dbg[((role * 256 + stage) * 8 + event)] = clock64(), CTA 0 only, first 256 stages
   // (compiled in only with -DSCN_TC_TIMELINE: the marks cost the single-warp issue loops real time)
   auto mark = [&](int role, int stage, int ev) {
@@ -401,20 +403,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
         const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
         if (lane_on) {
-          for (int p0 = 0; p0 < npass; p0 += 6) {          // 6 list entries are read before their copies are issued
-            int2 e[6];
+          if (!full) {
+            // hot path, ~6 instructions per item: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
+            for (int p0 = 0; p0 < npass; p0 += 6) {        // 6 list entries are read before their copies are issued
+              int2 e[6];
 #pragma unroll
-            for (int u = 0; u < 6; ++u) {
-              const int item = (p0 + u) * IPP + sub;
-              e[u] = make_int2(-1, 0);
-              if (item < nlive) e[u] = list[item];
-            }
-#pragma unroll
-            for (int u = 0; u < 6; ++u) {
-              if (e[u].y != 0) {
-                const bool live = e[u].x != -1 && !(p.exp & 1);     // .x: offset of the source row in 16-byte units, -1: zeros
-                cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e[u].x : 0u) << 4), live ? 16u : 0u);
+              for (int u = 0; u < 6; ++u) {
+                const int item = (p0 + u) * IPP + sub;
+                e[u] = make_int2(0, 0);
+                if (item < nlive) e[u] = list[item];
               }
+#pragma unroll
+              for (int u = 0; u < 6; ++u)
+                if (e[u].y != 0) cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(uint32_t)e[u].x << 4), 16u);
+            }
+          } else {
+            // first stage of a tile: every row is written, missing neighbours as zeros (src-size 0 reads nothing)
+            for (int pass = 0; pass < npass; ++pass) {
+              const int2 e = list[pass * IPP + sub];
+              const bool live = e.x != -1;
+              cp_async16((uint32_t)e.y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e.x : 0u) << 4), live ? 16u : 0u);
             }
           }
         }

@@ -1,4 +1,3 @@
 python tools/tc_timeline.py 150000 27 96 96 > gpurun_out/tl_96.txt 2>&1
-python tools/tc_timeline.py 500000 27 32 32 > gpurun_out/tl_32.txt 2>&1
 python tools/tc_timeline.py 317485 27 64 64 > gpurun_out/tl_64.txt 2>&1
-tail -n 2 gpurun_out/tl_96.txt gpurun_out/tl_32.txt gpurun_out/tl_64.txt
+tail -n 2 gpurun_out/tl_96.txt gpurun_out/tl_64.txt
