@@ -166,9 +166,33 @@ int scn_conv_wgrad(const void* in, int in_dtype, const void* dout, int dout_dtyp
                    int precision, float* dW, void* stream);
 
 
-/* dbias[c] = sum_rows dout[r][c]  (fp32 out, overwritten).  stats_ws: 2*C doubles of scratch. */
+/* dbias[c] = sum_rows dout[r][c]  (fp32 out, overwritten).  stats_ws: 2*C doubles of scratch.
+ * scn_col_sum_acc: out[c] += ... when accumulate != 0 (gradient accumulated in place). */
 int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out,
                 void* stream);
+int scn_col_sum_acc(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out,
+                    int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * One call per convolution module forward / backward (the X_updateOutput / X_backward pairs of
+ * SCN's SubmanifoldConvolution, Convolution and Deconvolution): weight re-layout, contraction(s)
+ * and bias-gradient reduction on caller-owned workspaces.
+ *   W: the module's fp32 parameter [K][Cin][Cout]; wimg / wimg_t: scn_conv_prep_bytes() bytes for
+ *   (K,Cin,Cout) / (K,Cout,Cin); skip_prep != 0 when the workspace already holds the image of
+ *   the current W.  Forward: out = bias + conv(x) through nbr.  Backward (each part optional,
+ *   NULL skips it): dx through nbr_bwd with W^T (mirror: W[K-1-k]^T, submanifold), dW += x^T dout
+ *   through nbr_fwd (zero_dW clears it first), dbias (+)= column sums of dout.
+ * ------------------------------------------------------------------------------------------ */
+int scn_conv_module_forward(const void* x, int x_dtype, int64_t n_in_rows, const int32_t* nbr,
+                            int K, int64_t n_out_rows, int64_t n_pad, int Cin, int Cout,
+                            const float* W, const float* bias, int precision, void* wimg,
+                            int skip_prep, void* out, int out_dtype, void* stream);
+int scn_conv_module_backward(const void* x, int x_dtype, int64_t n_in_rows, const void* dout,
+                             int dout_dtype, int64_t n_out_rows, const int32_t* nbr_fwd,
+                             int64_t n_pad_fwd, const int32_t* nbr_bwd, int64_t n_pad_bwd, int K,
+                             int Cin, int Cout, const float* W, int mirror, int precision,
+                             void* wimg_t, int skip_prep, void* dx, float* dW, int zero_dW,
+                             float* dbias, int accumulate_dbias, double* stats_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Bandwidth-bound layers.  Feature matrices are [n, C] row-major of `dtype`.
@@ -182,11 +206,12 @@ int scn_bn_forward(const void* x, int dtype, int64_t n, int C, const float* gamm
                    const float* beta, float* running_mean, float* running_var, int training,
                    float eps, float momentum, float leakiness, float* save_mean,
                    float* save_invstd, double* stats_ws, void* out, void* stream);
-/* dx, dgamma[C], dbeta[C] (fp32, overwritten).  `training` selects batch- or running-stat form. */
+/* dx, dgamma[C], dbeta[C] (fp32; overwritten, or accumulated into when accumulate_params != 0).
+ * `training` selects batch- or running-stat form. */
 int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C,
                     const float* gamma, const float* beta, const float* save_mean,
                     const float* save_invstd, int training, float leakiness, double* stats_ws,
-                    void* dx, float* dgamma, float* dbeta, void* stream);
+                    void* dx, float* dgamma, float* dbeta, int accumulate_params, void* stream);
 
 int scn_leaky_forward(const void* x, int dtype, int64_t count, float leak, void* out, void* stream);
 int scn_leaky_backward(const void* x, const void* dout, int dtype, int64_t count, float leak,

@@ -44,8 +44,12 @@ SIGNATURES = {
     "scn_conv_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p]),
     "scn_conv_wgrad": (_i, [_p, _i, _p, _i, _p, _i, _i64, _i64, _i, _i, _i, _p, _p]),
     "scn_col_sum": (_i, [_p, _i, _i64, _i, _p, _p, _p]),
+    "scn_col_sum_acc": (_i, [_p, _i, _i64, _i, _p, _p, _i, _p]),
+    "scn_conv_module_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
+    "scn_conv_module_backward": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p, _i, _i, _p, _i,
+                                      _p, _p, _i, _p, _i, _p, _p]),
     "scn_bn_forward": (_i, [_p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
-    "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _p]),
+    "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p]),
     "scn_leaky_forward": (_i, [_p, _i, _i64, _f, _p, _p]),
     "scn_leaky_backward": (_i, [_p, _p, _i, _i64, _f, _p, _p]),
     "scn_add_forward": (_i, [_p, _p, _i, _i64, _f, _p, _p]),

@@ -179,11 +179,11 @@ __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ do
   LoadVec<T, VEC>::st(dx + i * VEC, v);
 }
 
-__global__ void k_acc_to_float(const double* __restrict__ acc, int C, float* dgamma, float* dbeta) {
+__global__ void k_acc_to_float(const double* __restrict__ acc, int C, float* dgamma, float* dbeta, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dbeta) dbeta[c] = (float)acc[c];
-  if (dgamma) dgamma[c] = (float)acc[C + c];
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)acc[c];
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)acc[C + c];
 }
 
 template <typename T, int VEC>
@@ -330,7 +330,7 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
 template <typename T>
 int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamma, const float* beta,
                   const float* mean, const float* invstd, int training, float leak, double* ws, T* dx, float* dgamma,
-                  float* dbeta, cudaStream_t s) {
+                  float* dbeta, int accumulate, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
   if (n > 0) {
@@ -338,7 +338,7 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
                  : launch_col_reduce<1>(BnBwdF<T, 1>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s);
     if (rc) return rc;
   }
-  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta);
+  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, accumulate);
   SCN_LAUNCH_CHECK();
   if (n == 0) return SCN_OK;
   int64_t total = n * C;
@@ -395,19 +395,25 @@ extern "C" int scn_bn_forward(const void* x, int dtype, int64_t n, int C, const 
 
 extern "C" int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C, const float* gamma,
                                const float* beta, const float* save_mean, const float* save_invstd, int training,
-                               float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta, void* stream) {
+                               float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta,
+                               int accumulate_params, void* stream) {
   if (C < 1 || !save_mean || !save_invstd || !stats_ws) return SCN_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_T(dtype,
              return bn_backward_t<float>((const float*)x, (const float*)dout, n, C, gamma, beta, save_mean, save_invstd,
-                                         training, leakiness, stats_ws, (float*)dx, dgamma, dbeta, s),
+                                         training, leakiness, stats_ws, (float*)dx, dgamma, dbeta, accumulate_params, s),
              return bn_backward_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, n, C, gamma, beta,
                                                  save_mean, save_invstd, training, leakiness, stats_ws,
-                                                 (__nv_bfloat16*)dx, dgamma, dbeta, s));
+                                                 (__nv_bfloat16*)dx, dgamma, dbeta, accumulate_params, s));
   return SCN_OK;
 }
 
 extern "C" int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out, void* stream) {
+  return scn_col_sum_acc(x, dtype, n, C, stats_ws, out, 0, stream);
+}
+
+extern "C" int scn_col_sum_acc(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out, int accumulate,
+                               void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (C < 1 || !out || !stats_ws) return SCN_ERR_ARG;
   double* acc = stats_ws;
@@ -425,7 +431,7 @@ extern "C" int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* s
       rc = SCN_ERR_ARG;
   }
   if (rc != SCN_OK) return rc;
-  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(acc, C, nullptr, out);
+  k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(acc, C, nullptr, out, accumulate);
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }

@@ -143,12 +143,22 @@ class Pending:
 class SparseConvNetTensor:
     """features [nActive, C] + shared metadata + spatial_size (LongTensor), as in SCN."""
 
-    def __init__(self, features=None, metadata=None, spatial_size=None, pending=None):
+    def __init__(self, features=None, metadata=None, spatial_size=None, pending=None, _sp=None):
         self._features = features
         self._pending = pending
         self._taken = None
         self.metadata = metadata
-        self.spatial_size = spatial_size
+        self._spatial_size = spatial_size
+        self._spc = _sp            # spatial_size as a tuple of ints (reading a LongTensor element-wise costs microseconds)
+
+    @property
+    def spatial_size(self):
+        return self._spatial_size
+
+    @spatial_size.setter
+    def spatial_size(self, value):
+        self._spatial_size = value
+        self._spc = None
 
     @property
     def features(self):
@@ -173,7 +183,10 @@ class SparseConvNetTensor:
         return pend
 
     def _sp(self):
-        return tuple(int(v) for v in self.spatial_size)
+        c = self._spc
+        if c is None:
+            c = self._spc = tuple(int(v) for v in self._spatial_size)
+        return c
 
     def get_spatial_locations(self, spatial_size=None):
         sp = self._sp() if spatial_size is None else tuple(int(v) for v in spatial_size)

@@ -14,62 +14,156 @@ def _w3(weight):
     return weight.detach().reshape(weight.shape[0], weight.shape[-2], weight.shape[-1]).contiguous().float()
 
 
+def _direct_grad(param):
+    """The gradient buffer to accumulate into in place, when the owner of the parameter asked for it
+    (trainer.FlatGradArena marks parameters with ``_scn_direct_grad``): saves the separate dW tensor, its zero fill and
+    autograd's AccumulateGrad add for every parameter of the sparse network."""
+    if param is None or not getattr(param, "_scn_direct_grad", False):
+        return None
+    g = param.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.device != param.device:
+        return None
+    return g
+
+
+def _grad_ready(param):
+    cb = getattr(param, "_scn_grad_ready", None)
+    if cb is not None:
+        cb(param)
+
+
+class ConvWorkspace:
+    """Per-module device workspaces of the convolution kernels: the re-laid weight images for the forward and for the
+    dgrad, each tagged with the (version, storage) of the weight it was built from so unchanged weights are not
+    re-laid (inference, gradient accumulation), and the kernel family chosen for this shape."""
+
+    __slots__ = ("fwd", "bwd", "fwd_key", "bwd_key", "path")
+
+    def __init__(self, K, cin, cout, prec, dtype, device):
+        self.fwd = torch.empty((ops.conv_prep_bytes(K, cin, cout, prec, dtype),), dtype=torch.uint8, device=device)
+        self.bwd = None
+        self.fwd_key = self.bwd_key = None
+        self.path = ops.conv_path(K, cin, cout, prec, dtype)
+
+    def bwd_buffer(self, K, cin, cout, prec, dtype, device):
+        if self.bwd is None:
+            self.bwd = torch.empty((ops.conv_prep_bytes(K, cout, cin, prec, dtype),), dtype=torch.uint8, device=device)
+        return self.bwd
+
+
 class ConvFn(Function):
     """out[o] = bias + sum_k x[nbr_fwd[k][o]] @ W[k].
 
     mirror=True  (submanifold): dgrad uses the same table with B_k = W[K-1-k]^T.
     mirror=False (strided / deconvolution): dgrad uses nbr_bwd (the transposed table) with W[k]^T.
+    `owner` (the module) keeps the weight-image workspaces; with it, forward and backward are ONE C-ABI call each.
     """
 
     @staticmethod
-    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror):
+    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner=None):
         x = x.contiguous()
         prec = config.precision_code()
-        w3 = _w3(weight)
-        K, cin, cout = w3.shape
-        bprep = ops.prep_weights(w3, False, False, prec, config.feature_dtype())
-        b = bias.detach().float().contiguous() if bias is not None else None
-        out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, config.feature_dtype())
-        ctx.save_for_backward(x, weight)
+        fdt = config.feature_dtype()
+        K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
+        fat = (owner is not None and not ops.profiling() and weight.dtype == torch.float32 and weight.is_contiguous()
+               and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous())))
+        ctx.fat = fat
+        if fat:
+            ws = owner.workspace(K, cin, cout, prec, fdt, x.device)
+            if ws.path > 0 and x.dtype != fdt:
+                x = ops.convert(x, fdt)
+            key = (weight._version, weight.data_ptr())
+            out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd,
+                                          ws.fwd_key == key)
+            ws.fwd_key = key
+            ctx.ws = ws
+        else:
+            w3 = _w3(weight)
+            bprep = ops.prep_weights(w3, False, False, prec, fdt)
+            b = bias.detach().float().contiguous() if bias is not None else None
+            out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, fdt)
+        ctx.save_for_backward(x, weight, bias)
         ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.prec = nbr_fwd, nbr_bwd, mirror, prec
-        ctx.has_bias = bias is not None
         ctx.n_out_rows = n_out_rows
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight = ctx.saved_tensors
+        x, weight, bias = ctx.saved_tensors
         dout = dout.contiguous()
-        w3 = _w3(weight)
-        K, cin, cout = w3.shape
+        K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = bias is not None and ctx.needs_input_grad[2]
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.fat:
+            ws = ctx.ws
+            xw = x
+            if ws.path > 0 and x.dtype != dout.dtype:
+                xw = ops.convert(x, dout.dtype)
+            # parameter gradients: straight into .grad when the trainer asked for it, else into fresh buffers
+            gw = _direct_grad(weight) if need_dw else None
+            gb = _direct_grad(bias) if need_db else None
+            if need_dw and gw is None:
+                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+            if need_db and gb is None:
+                db = torch.empty(bias.shape, dtype=torch.float32, device=x.device)
+            wimg_t, skip = None, False
+            if need_dx:
+                wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
+                key = (weight._version, weight.data_ptr())
+                skip = ws.bwd_key == key
+                ws.bwd_key = key
+            dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
+                                          ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
+                                          gw if gw is not None else dw, gw is None,
+                                          gb if gb is not None else db, gb is not None)
+            if dx is not None and dx.dtype != x.dtype:
+                dx = ops.convert(dx, x.dtype)
+            if gw is not None:
+                _grad_ready(weight)
+            if gb is not None:
+                _grad_ready(bias)
+            return dx, dw, db, None, None, None, None, None
+        w3 = _w3(weight)
+        if need_dx:
             bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec, x.dtype)
             dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
                                   kind="conv_dgrad")
-        if ctx.needs_input_grad[1]:
+        if need_dw:
             dw = ops.conv_wgrad(x, dout, ctx.nbr_fwd, ctx.n_out_rows, cin, cout, ctx.prec).view_as(weight)
             dw = dw.to(weight.dtype)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
+        if need_db:
             db = ops.col_sum(dout)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 class BatchNormFn(Function):
     @staticmethod
     def forward(ctx, x, weight, bias, running_mean, running_var, training, eps, momentum, leak):
         x = x.contiguous()
-        g = weight.detach().float().contiguous() if weight is not None else None
-        b = bias.detach().float().contiguous() if bias is not None else None
-        out, mean, invstd = ops.bn_forward(x, g, b, running_mean, running_var, training, eps, momentum, leak)
-        ctx.save_for_backward(x, g, b, mean, invstd)
+        lean = weight is None or (weight.dtype == torch.float32 and weight.is_contiguous()
+                                  and bias.dtype == torch.float32 and bias.is_contiguous())
+        g = weight if lean else weight.detach().float().contiguous()
+        b = bias if lean else bias.detach().float().contiguous()
+        out, stats = ops.bn_forward(x, g, b, running_mean, running_var, training, eps, momentum, leak)
+        ctx.save_for_backward(x, g, b, stats)
+        ctx.params = (weight, bias) if lean and weight is not None else None
         ctx.training, ctx.leak, ctx.affine = training, leak, weight is not None
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, g, b, mean, invstd = ctx.saved_tensors
-        dx, dg, db = ops.bn_backward(x, dout.contiguous(), g, b, mean, invstd, ctx.training, ctx.leak)
+        x, g, b, stats = ctx.saved_tensors
+        gw = gb = None
+        if ctx.params is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            gw, gb = _direct_grad(ctx.params[0]), _direct_grad(ctx.params[1])
+            if gw is None or gb is None:
+                gw = gb = None
+        dx, dg, db = ops.bn_backward(x, dout.contiguous(), g, b, stats, ctx.training, ctx.leak, gw, gb)
+        if gw is not None:
+            _grad_ready(ctx.params[0])
+            _grad_ready(ctx.params[1])
+            dg = db = None
         if not ctx.affine:
             dg = db = None
         return dx, dg, db, None, None, None, None, None, None

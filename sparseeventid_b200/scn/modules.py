@@ -24,8 +24,17 @@ def _volume(t):
     return v
 
 
+def _mark(*params):
+    """Tags parameters whose gradients the kernels can accumulate in place (see trainer.FlatGradArena)."""
+    for p in params:
+        if p is not None:
+            p._scn_param = True
+
+
 def _new_like(input, features, spatial_size=None):
-    return SparseConvNetTensor(features, input.metadata, input.spatial_size if spatial_size is None else spatial_size)
+    if spatial_size is None:
+        return SparseConvNetTensor(features, input.metadata, input.spatial_size, None, input._spc)
+    return SparseConvNetTensor(features, input.metadata, spatial_size)
 
 
 class InputLayer(nn.Module):
@@ -61,11 +70,10 @@ class InputLayer(nn.Module):
         md.row_of_input = rows
         md.n_input = int(keys.shape[0])
         md.input_spatial = sp
-        if lvl.n > 0:
-            max_b = int((keys_out.max() >> 48).item())
-            md.batch_size = max(batch_size, max_b + 1)
+        if batch_size > 0 or lvl.n == 0:
+            md.batch_size = batch_size            # given by the caller (the reference always passes it): no device sync
         else:
-            md.batch_size = batch_size
+            md.batch_size = int((keys_out.max() >> 48).item()) + 1
         out = SparseConvNetTensor(None, md, self.spatial_size)
         out.features = F.InputLayerFn.apply(feats, rows, lvl.n, self.mode)
         return out
@@ -92,6 +100,7 @@ class _ConvBase(nn.Module):
         w.normal_(0, math.sqrt(2.0 / (nIn * k)))
         self.weight = nn.Parameter(w)
         self.bias = nn.Parameter(torch.zeros(nOut)) if bias else None
+        _mark(self.weight, self.bias)
 
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         # accept SCN 2018-19 checkpoints whose conv weights are [K, Cin, Cout]
@@ -100,6 +109,15 @@ class _ConvBase(nn.Module):
             w = state_dict[key]
             state_dict[key] = w.reshape(w.shape[0], 1, w.shape[1], w.shape[2])
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def workspace(self, K, cin, cout, prec, dtype, device):
+        """Device workspaces of this module's kernels (weight images), created on first use; not part of state_dict."""
+        table = self.__dict__.setdefault("_scn_ws", {})
+        key = (prec, dtype, device)
+        ws = table.get(key)
+        if ws is None:
+            ws = table[key] = F.ConvWorkspace(K, cin, cout, prec, dtype, device)
+        return ws
 
     def _check(self, input):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, \
@@ -124,7 +142,7 @@ class SubmanifoldConvolution(_ConvBase):
         md = input.metadata
         nbr = md.subm_table(input._sp(), self.filter_size)
         n = md.levels[input._sp()].n
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, nbr, nbr, n, True)
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, nbr, nbr, n, True, self)
         return _new_like(input, feats)
 
     def __repr__(self):
@@ -148,7 +166,7 @@ class Convolution(_ConvBase):
         self._check(input)
         md = input.metadata
         rule = md.strided_rule(input._sp(), self.filter_size, self.filter_stride)
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.down, rule.up, rule.n_out, False)
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.down, rule.up, rule.n_out, False, self)
         return _new_like(input, feats, torch.LongTensor(list(rule.out_spatial)))
 
     def __repr__(self):
@@ -177,7 +195,7 @@ class Deconvolution(_ConvBase):
         if fine not in md.levels:
             raise RuntimeError("Deconvolution needs the fine grid to exist in the metadata")
         rule = md.strided_rule(fine, self.filter_size, self.filter_stride)
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.up, rule.down, rule.n_in, False)
+        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.up, rule.down, rule.n_in, False, self)
         return _new_like(input, feats, torch.LongTensor(list(fine)))
 
 
@@ -193,6 +211,7 @@ class BatchNormalization(nn.Module):
         if affine:
             self.weight = nn.Parameter(torch.ones(nPlanes))
             self.bias = nn.Parameter(torch.zeros(nPlanes))
+            _mark(self.weight, self.bias)
         else:
             self.register_parameter("weight", None)
             self.register_parameter("bias", None)
@@ -207,7 +226,7 @@ class BatchNormalization(nn.Module):
                                        float(self.eps), float(self.momentum), leak)
         if config.fusion_enabled() and float(self.leakiness) == 1.0:
             # defer by one module: a following LeakyReLU/ReLU becomes the fused leakiness of this same kernel
-            return SparseConvNetTensor(None, input.metadata, input.spatial_size, Pending("bn", run, run))
+            return SparseConvNetTensor(None, input.metadata, input.spatial_size, Pending("bn", run, run), input._spc)
         return _new_like(input, run())
 
     def __repr__(self):
@@ -271,7 +290,8 @@ class AddTable(nn.Module):
 
             def fuse(leak):
                 return F.AddLeakyFn.apply(a, b, leak)
-            return SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size, Pending("add", run, fuse))
+            return SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size, Pending("add", run, fuse),
+                                       input[0]._spc)
         feats = input[0].features
         for t in input[1:]:
             feats = F.AddFn.apply(feats, t.features)

@@ -52,6 +52,22 @@ def set_profiler(p):
     _profiler = p
 
 
+def profiling() -> bool:
+    return _profiler is not None
+
+
+_scratch = {}
+
+
+def stats_scratch(device, c: int) -> torch.Tensor:
+    """fp64 [2*C] scratch of the column reductions: one buffer per device shared by every layer (stream-ordered)."""
+    t = _scratch.get(device)
+    if t is None or t.numel() < 2 * c:
+        t = torch.empty((max(2 * c, 2048),), dtype=torch.float64, device=device)
+        _scratch[device] = t
+    return t
+
+
 def _i32(n, device):
     return torch.empty((n,), dtype=torch.int32, device=device)
 
@@ -238,6 +254,36 @@ def conv_wgrad(x, dout, nbr, n_rows, n_in, n_out, prec) -> torch.Tensor:
     return dw
 
 
+def conv_prep_bytes(K, n_in, n_out, prec, feat_dtype) -> int:
+    return int(L.lib().scn_conv_prep_bytes(K, n_in, n_out, prec, _DT[feat_dtype]))
+
+
+def conv_module_forward(x, weight, bias, nbr, n_out_rows, K, cin, cout, prec, out_dtype, wimg, skip_prep) -> torch.Tensor:
+    """One C-ABI call: weight re-layout into `wimg` (unless skip_prep) + out = bias + conv(x).  weight/bias fp32."""
+    out = torch.empty((n_out_rows, cout), dtype=out_dtype, device=x.device)
+    L.check(L.lib().scn_conv_module_forward(x.data_ptr(), _DT[x.dtype], x.shape[0], nbr.data_ptr(), K, n_out_rows,
+                                            nbr.shape[1], cin, cout, weight.data_ptr(),
+                                            None if bias is None else bias.data_ptr(), prec, wimg.data_ptr(),
+                                            int(skip_prep), out.data_ptr(), _DT[out_dtype], L.stream()),
+            "scn_conv_module_forward")
+    return out
+
+
+def conv_module_backward(x, dout, weight, nbr_fwd, nbr_bwd, n_out_rows, K, cin, cout, mirror, prec, wimg_t, skip_prep,
+                         need_dx, dw, zero_dw, dbias, accumulate_dbias):
+    """One C-ABI call: dx (returned, or None), dW accumulated into `dw`, dbias (+)= column sums.  Any part may be None."""
+    dx = torch.empty((x.shape[0], cin), dtype=x.dtype, device=x.device) if need_dx else None
+    ws = stats_scratch(x.device, cout) if dbias is not None else None
+    L.check(L.lib().scn_conv_module_backward(
+        x.data_ptr(), _DT[x.dtype], x.shape[0], dout.data_ptr(), _DT[dout.dtype], n_out_rows,
+        nbr_fwd.data_ptr(), nbr_fwd.shape[1], nbr_bwd.data_ptr(), nbr_bwd.shape[1], K, cin, cout, weight.data_ptr(),
+        int(mirror), prec, None if wimg_t is None else wimg_t.data_ptr(), int(skip_prep),
+        None if dx is None else dx.data_ptr(), None if dw is None else dw.data_ptr(), int(zero_dw),
+        None if dbias is None else dbias.data_ptr(), int(accumulate_dbias), None if ws is None else ws.data_ptr(),
+        L.stream()), "scn_conv_module_backward")
+    return dx
+
+
 def col_sum(x) -> torch.Tensor:
     n, c = x.shape
     ws = torch.empty((2 * c,), dtype=torch.float64, device=x.device)
@@ -250,34 +296,40 @@ def col_sum(x) -> torch.Tensor:
 
 
 def bn_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak):
+    """-> (out, stats) with stats fp32 [2, C] = (mean, invstd) used by the backward."""
     n, c = x.shape
     dev = x.device
-    save_mean = torch.empty((c,), dtype=torch.float32, device=dev)
-    save_invstd = torch.empty((c,), dtype=torch.float32, device=dev)
-    ws = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    stats = torch.empty((2, c), dtype=torch.float32, device=dev)
+    ws = stats_scratch(dev, c)
     out = torch.empty_like(x)
     p = _profiler
     e0 = p.begin() if p else None
-    L.check(L.lib().scn_bn_forward(L.ptr(x), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta), L.ptr(rm), L.ptr(rv),
-                                   int(training), eps, momentum, leak, L.ptr(save_mean), L.ptr(save_invstd),
-                                   L.ptr(ws), L.ptr(out), L.stream()), "scn_bn_forward")
+    sp = stats.data_ptr()
+    L.check(L.lib().scn_bn_forward(x.data_ptr(), _DT[x.dtype], n, c, L.ptr(gamma), L.ptr(beta), rm.data_ptr(),
+                                   rv.data_ptr(), int(training), eps, momentum, leak, sp, sp + 4 * c, ws.data_ptr(),
+                                   out.data_ptr(), L.stream()), "scn_bn_forward")
     if p:   # stats pass reads x, apply pass reads x and writes out
         p.end(e0, kind="bn_fwd", bytes=3.0 * x.numel() * x.element_size())
-    return out, save_mean, save_invstd
+    return out, stats
 
 
-def bn_backward(x, dout, gamma, beta, save_mean, save_invstd, training, leak):
+def bn_backward(x, dout, gamma, beta, stats, training, leak, dgamma=None, dbeta=None):
+    """-> (dx, dgamma, dbeta).  When dgamma/dbeta buffers are given the parameter gradients are ACCUMULATED into them."""
     n, c = x.shape
     dev = x.device
-    ws = torch.empty((2 * c,), dtype=torch.float64, device=dev)
+    ws = stats_scratch(dev, c)
     dx = torch.empty_like(x)
-    dgamma = torch.empty((c,), dtype=torch.float32, device=dev)
-    dbeta = torch.empty((c,), dtype=torch.float32, device=dev)
+    accumulate = dgamma is not None
+    if not accumulate:
+        both = torch.empty((2, c), dtype=torch.float32, device=dev)
+        dgamma, dbeta = both[0], both[1]
     p = _profiler
     e0 = p.begin() if p else None
-    L.check(L.lib().scn_bn_backward(L.ptr(x), L.ptr(dout), L.dtype_code(x), n, c, L.ptr(gamma), L.ptr(beta),
-                                    L.ptr(save_mean), L.ptr(save_invstd), int(training), leak, L.ptr(ws), L.ptr(dx),
-                                    L.ptr(dgamma), L.ptr(dbeta), L.stream()), "scn_bn_backward")
+    sp = stats.data_ptr()
+    L.check(L.lib().scn_bn_backward(x.data_ptr(), dout.data_ptr(), _DT[x.dtype], n, c, L.ptr(gamma), L.ptr(beta),
+                                    sp, sp + 4 * c, int(training), leak, ws.data_ptr(), dx.data_ptr(),
+                                    dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate), L.stream()),
+            "scn_bn_backward")
     if p:   # reduce pass reads x,dout; apply pass reads x,dout and writes dx
         p.end(e0, kind="bn_bwd", bytes=5.0 * x.numel() * x.element_size())
     return dx, dgamma, dbeta

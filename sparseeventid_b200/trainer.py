@@ -48,8 +48,16 @@ class FlatGradArena:
         self._pending = [0] * len(self.buckets)
         self._works = []
         self._hooks = []
-        if self.world > 1:
-            for p in self.params:
+        # Parameters of the sparse modules get their gradients ACCUMULATED IN PLACE by the kernels (wgrad atomics,
+        # BatchNorm / bias column sums) straight into the arena: no dW temporaries, no zero fills, no AccumulateGrad
+        # adds (218 small launches per step).  Those never reach autograd's accumulation hook, so the functions call
+        # `_scn_grad_ready` themselves; every other parameter (the dense heads) uses the normal hook.
+        for p in self.params:
+            if getattr(p, "_scn_param", False):
+                p._scn_direct_grad = True
+                if self.world > 1:
+                    p._scn_grad_ready = self._on_grad
+            elif self.world > 1:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     def zero(self):
