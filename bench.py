@@ -290,7 +290,7 @@ def run_ours(args, rank, world, local_rank):
             t = sum(r["ms"] for r in tc) * 1e-3
             peak = peaks["bf16_tflops_sustained"]
             traffic, traffic_note = None, None
-            prof_path = os.path.join(ROOT, "profiles", "r01_conv_tc_ncu_summary.json")
+            prof_path = os.path.join(ROOT, "profiles", "r01b_conv_tc_ncu_summary.json")
             if os.path.exists(prof_path):      # dram bytes of ONE ncu --set full capture of this kernel (committed)
                 pj = json.load(open(prof_path))
                 traffic = pj.get("traffic_bytes_per_launch")

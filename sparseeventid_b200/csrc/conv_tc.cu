@@ -1,29 +1,34 @@
 // Output-stationary gather-GEMM convolution on 5th-generation tensor cores (sm_100a only):
 //     out[o, :] = bias + sum_k  in[nbr[k][o], :] . B_k            (bf16 operands, fp32 accumulate)
 //
-// One persistent CTA per SM walks GROUPS of T 128-row output tiles (T * n_out <= 256 TMEM columns,
-// two groups double-buffered in the 512 columns).  The contraction (K offsets x n_in channels) is cut
-// into stages of 64 channels (one 128-byte shared-memory row).  For every stage q = (offset, chunk):
-//   * the weight tile B(q) (n_out x 128 B, pre-swizzled image) is streamed ONCE per group by a 1-D bulk
-//     async copy (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
-//   * for each tile ONE producer warp gathers the stage: it reads the tile's 128 neighbour indices (prefetched one
-//     stage ahead), ballots them, compacts the LIVE rows into a warp-private list and moves only those rows
-//     (8 lanes per 128-byte row, coalesced 16-byte LDG -> STS.128 into the 128B-swizzled K-major A tile, up to
-//     G passes of loads in flight).  The ballots are published as the stage's disable-output-lane mask,
-//   * 1 thread issues tcgen05.mma (M=128, N=n_out, K=16) with that mask: accumulator rows without a neighbour at
-//     this offset are not updated, so their (stale) A rows are never read into a result.  Only the first stage of
-//     a tile, which initialises the accumulator, is written in full (zeros for missing neighbours),
-//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store while the
-//     next group's MMAs run into the other TMEM half.
+// One persistent CTA per SM owns a contiguous range of 128-row output tiles (an even split of the tiles over the
+// grid) and walks it in GROUPS of T tiles whose accumulators live in TMEM together (T * n_out <= 256 columns with two
+// groups double-buffered, or <= 512 columns single-buffered when a CTA has one group anyway).  The contraction
+// (K offsets x n_in channels) is cut into stages of 64 channels (one 128-byte shared-memory row).  Per stage:
+//   * the weight tile B(q) (n_out x 128 B, pre-swizzled image) is streamed ONCE per group by a 1-D bulk async copy
+//     (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
+//   * for each tile ONE producer warp gathers the A tile: it reads the tile's 128 neighbour indices (prefetched one
+//     stage ahead), ballots them, compacts the LIVE rows into a warp-private list of (source offset, swizzled
+//     destination) pairs and copies only those rows with 16-byte LDGSTS (8 lanes per 128-byte row).  The ballots are
+//     published as the stage's disable-output-lane mask.  The copies signal their landing themselves
+//     (cp.async.mbarrier.arrive.noinc), the warp never waits for them and alternates between its two A slots,
+//   * up to 4 issuing warps (tile t -> warp t mod NM) issue tcgen05.mma (M=128, N=n_out, K=16) with that mask:
+//     accumulator rows without a neighbour at this offset are not updated, so their stale A rows never reach a
+//     result.  Only the first stage of a tile, which initialises the accumulator, is written in full,
+//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store.
 // Every output row is written exactly once: no atomics, deterministic.
 //
-// Each producer warp owns one A slot (stage n -> warp/slot n mod SA): consecutive uses of a slot's two mbarriers are
-// then consecutive phases, which parity waits require.  SA warps gather SA stages concurrently; a stage costs its
-// warp one L2 round trip, so per-SM gather throughput is SA stages per round trip and moves only live bytes.
+// Synchronisation notes.  A slot's mbarriers must see consecutive phases from each waiter (a parity wait cannot tell
+// phase r from r-2), hence one producer warp per pair of slots; the issuing warps run up to SA stages apart, so the
+// "which stage is in this slot" handshake is a monotonically increasing sequence flag (release store / acquire poll)
+// and only then the landing barrier, whose parity the flag carries.
 //
-// History (profiles/): dense zero-filled A tiles via 16-byte cp.async (~950 cycles per 16 KB stage),
-// TMA tile::gather4 (~77 cycles per 512-byte instruction) and lock-step LDG/STS batches were measured first; all
-// were bound by moving 128 rows per stage although ~30% are live.
+// What bounds it (timeline marks, -DSCN_TC_TIMELINE + tools/tc_timeline.py): neither L2 latency
+// nor the tensor pipe but the dependent-issue rate of the single warps that build a stage (~5 cycles per
+// instruction), so every role's per-stage instruction count was cut (6 instructions per gathered row segment,
+// ~70 per issued stage) and the roles were multiplied (5-6 producer warps, 4 issuing warps).
+// History (profiles/): dense zero-filled A tiles via cp.async, TMA tile::gather4 and lock-step LDG/STS batches
+// were measured first; they moved all 128 rows per stage although ~30% are live.
 //
 // Replaces SCN's dConvolution_KMxKN_forwardA/B; reference call sites
 // src/networks/sparse_building_blocks.py:29-34,110-117.

@@ -7,6 +7,7 @@ It is shared by reference by every tensor derived from one InputLayer call.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Tuple
 
@@ -56,10 +57,62 @@ class StridedRule:
     n_out: int
 
 
+_side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
+_side_enabled = os.environ.get("SCN_B200_RULEBOOK_STREAM", "1") not in ("0", "false", "False")
+
+
+def set_rulebook_stream(flag: bool) -> None:
+    """Rulebooks on their own CUDA stream (default) or on the caller's stream."""
+    global _side_enabled
+    _side_enabled = bool(flag)
+
+
+class _RulebookStream:
+    """Context: hash / rulebook work runs on a per-device side stream.
+
+    Rulebooks depend only on coordinates, never on features, but sizing the next level needs a row count on the
+    host.  On the caller's stream that read-back waits for every feature kernel queued so far (milliseconds of
+    convolutions) and the GPU then idles until the host has refilled the queue; on a side stream it waits for the
+    rulebook kernels alone, and those overlap the feature kernels.  On exit the caller's stream is made to wait for
+    the side stream's event, and every tensor produced inside is registered with the caller's stream
+    (``record_stream``) so the caching allocator does not recycle it while feature kernels still read it."""
+
+    def __init__(self, md, join_first=False):
+        self.md, self.join_first = md, join_first
+
+    def __enter__(self):
+        md = self.md
+        self.main = torch.cuda.current_stream(md.device)
+        self.active = _side_enabled and md.device.type == "cuda"
+        if self.active:
+            side = _side_streams.get(md.device)
+            if side is None:
+                side = _side_streams[md.device] = torch.cuda.Stream(device=md.device)
+            self.side = side
+            if self.join_first:              # the coordinates were produced on the caller's stream
+                side.wait_stream(self.main)
+            torch.cuda.set_stream(side)
+        return self
+
+    def publish(self, *tensors):
+        if self.active:
+            for t in tensors:
+                if t is not None:
+                    t.record_stream(self.main)
+        return tensors[0] if len(tensors) == 1 else tensors
+
+    def __exit__(self, *exc):
+        if self.active:
+            ev = self.side.record_event()
+            torch.cuda.set_stream(self.main)
+            self.main.wait_event(ev)
+        return False
+
+
 class Metadata:
     def __init__(self, dimension: int, device):
         self.dimension = dimension
-        self.device = device
+        self.device = torch.device(device)
         self.levels: Dict[Tuple[int, ...], Level] = {}
         self.subm: Dict[tuple, torch.Tensor] = {}
         self.strided: Dict[tuple, StridedRule] = {}
@@ -69,6 +122,9 @@ class Metadata:
         self.input_spatial = None
 
     # -- levels ------------------------------------------------------------------------------
+    def rulebook_stream(self, join_first=False) -> _RulebookStream:
+        return _RulebookStream(self, join_first)
+
     def add_level(self, spatial, keys, table=None):
         n = int(keys.shape[0])
         if table is None:
@@ -89,7 +145,9 @@ class Metadata:
         key = (tuple(spatial), tuple(filt))
         if key not in self.subm:
             lvl = self.levels[tuple(spatial)]
-            self.subm[key] = ops.subm_rulebook(lvl.keys, lvl.table_keys, lvl.table_vals, lvl.cap, pad3(filt, 1))
+            with self.rulebook_stream() as rs:
+                self.subm[key] = rs.publish(
+                    ops.subm_rulebook(lvl.keys, lvl.table_keys, lvl.table_vals, lvl.cap, pad3(filt, 1)))
         return self.subm[key]
 
     def strided_rule(self, spatial, filt, stride) -> StridedRule:
@@ -108,20 +166,22 @@ class Metadata:
             out_spatial.append((spatial[a] - filt[a]) // stride[a] + 1)
         out_spatial = tuple(out_spatial)
         lvl = self.levels[spatial]
-        keys_out, out_row, off = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
-        if out_spatial in self.levels:
-            # coarse grid already exists (e.g. built through another path): re-index onto its rows
-            have = self.levels[out_spatial]
-            remap = ops.hash_lookup(keys_out, have.table_keys, have.table_vals, have.cap)
-            out_row = remap[out_row.long()].contiguous()
-            n_out = have.n
-        else:
-            self.add_level(out_spatial, keys_out.clone())
-            n_out = int(keys_out.shape[0])
-        K = 1
-        for f in filt:
-            K *= f
-        down, up = ops.strided_tables(out_row, off, K, lvl.n, n_out)
+        with self.rulebook_stream() as rs:
+            keys_out, out_row, off = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
+            if out_spatial in self.levels:
+                # coarse grid already exists (e.g. built through another path): re-index onto its rows
+                have = self.levels[out_spatial]
+                remap = ops.hash_lookup(keys_out, have.table_keys, have.table_vals, have.cap)
+                out_row = remap[out_row.long()].contiguous()
+                n_out = have.n
+            else:
+                new = self.add_level(out_spatial, keys_out.clone())
+                rs.publish(new.keys, new.table_keys, new.table_vals)
+                n_out = int(keys_out.shape[0])
+            K = 1
+            for f in filt:
+                K *= f
+            down, up = rs.publish(*ops.strided_tables(out_row, off, K, lvl.n, n_out))
         rule = StridedRule(out_spatial, down, up, K, lvl.n, n_out)
         self.strided[key] = rule
         return rule

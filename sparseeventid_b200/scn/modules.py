@@ -63,10 +63,12 @@ class InputLayer(nn.Module):
         if coords.dim() != 2 or coords.shape[1] not in (self.dimension, self.dimension + 1):
             raise ValueError(f"coords must be [N, {self.dimension}] or [N, {self.dimension + 1}]")
         md = Metadata(self.dimension, feats.device)
-        keys = ops.pack_coords(coords, self.dimension)
-        rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
         sp = tuple(int(v) for v in self.spatial_size)
-        lvl = md.add_level(sp, keys_out, (tk, tv, cap))
+        with md.rulebook_stream(join_first=True) as rs:
+            keys = ops.pack_coords(coords, self.dimension)
+            rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
+            lvl = md.add_level(sp, keys_out, (tk, tv, cap))
+            rs.publish(rows, keys_out, tk, tv)
         md.row_of_input = rows
         md.n_input = int(keys.shape[0])
         md.input_spatial = sp
