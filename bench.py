@@ -36,6 +36,7 @@ import torch
 import torch.distributed as dist
 
 METRIC = "3D sparse ResNet train events/sec"
+METRIC_2D = "2D multiplane sparse ResNet train events/sec"   # --dataset dune2d (BASELINE.json configs[1])
 UNIT = "events/s"
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -162,7 +163,7 @@ def run_reference(args, rank):
     sample = (f"{events} synthetic {args.dataset} events per step (bounded sample of the batch-{args.batch} workload), "
               f"{args.steps} timed steps after {min(args.warmup, 1)} warm-up, fp32")
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if args.dataset == "dune3d" else METRIC_2D, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.dataset} default encoder+heads training step, CPU, {events} events/step",
@@ -322,7 +323,8 @@ def run_ours(args, rank, world, local_rank):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.dataset == "dune3d" else METRIC_2D, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
             "config": {"workload": f"{args.dataset} default encoder (56 sparse convs, 20.9M params) + 4 heads, training "

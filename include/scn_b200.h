@@ -230,6 +230,21 @@ int scn_rows_gather(const void* src, int dtype, const int32_t* rows, int64_t n_r
 int scn_rows_scatter_add(const void* src, int dtype, const int32_t* rows, int64_t n_rows, int C,
                          float* out_f32, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * larcv batch-filler array -> SCN input tuple on the device (replaces the host numpy transforms
+ * larcvsparse_to_scnsparse_3d / _2d, src/io/data_transforms.py:21-49,198-252).
+ * larcv: fp32 [B][P][V][ncol], last column = value, padding rows have value == pad_value (-999).
+ * scn_larcv_count: counts[p*B + b] = live rows of (sample b, plane p).  The caller turns them into
+ * exclusive offsets (plane-major order, which is the reference's row order) and allocates N rows.
+ * scn_larcv_compact: order-preserving compaction; layout 0 (3-D): coords4 = (x, y, z, b);
+ * layout 1 (2-D): coords4 = (plane, y, x, b); features[N] = value.
+ * ------------------------------------------------------------------------------------------ */
+int scn_larcv_count(const float* larcv, int B, int P, int V, int ncol, float pad_value,
+                    int32_t* counts, void* stream);
+int scn_larcv_compact(const float* larcv, int B, int P, int V, int ncol, float pad_value,
+                      const int64_t* row_offsets, int layout, int32_t* coords4, float* features,
+                      void* stream);
+
 /* SparseToDense: dense[b][c][x0][x1][x2] (fp32, zero-filled inside) <- x[row][c]; backward gathers. */
 int scn_sparse_to_dense_forward(const void* x, int dtype, const uint64_t* keys, int64_t n, int C,
                                 int batch, int s0, int s1, int s2, float* dense, void* stream);

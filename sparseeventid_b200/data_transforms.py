@@ -45,3 +45,47 @@ def larcvsparse_to_scnsparse_2d(input_array):
         all_coords.append(numpy.stack([pl, y, x, keep[0]], axis=-1))
         all_features.append(numpy.expand_dims(value[keep], axis=-1))
     return [numpy.concatenate(all_coords), numpy.concatenate(all_features), batch_size]
+
+
+# ------------------------------------------------------------------------------------------------
+# Device-side twins: same outputs, same row order, no host pass.  The pinned larcv buffer is
+# copied to the GPU as it is; the compaction runs in libscn_b200.so.  Coordinates come back as int32 [N, 4] on the
+# device (scn.InputLayer takes any integer or floating dtype), features as fp32 [N, 1].
+# ------------------------------------------------------------------------------------------------
+
+
+def _larcv_to_scn_gpu(input_array, layout):
+    import torch
+
+    from . import _lib as L
+    t = torch.as_tensor(input_array)
+    L.require_cuda(t, "larcvsparse_to_scnsparse_gpu")
+    t = t.contiguous().float()
+    B, P, V, ncol = t.shape
+    lib = L.lib()
+    counts = torch.empty((P * B,), dtype=torch.int32, device=t.device)
+    L.check(lib.scn_larcv_count(t.data_ptr(), B, P, V, ncol, float(PAD_VALUE), counts.data_ptr(), L.stream()),
+            "scn_larcv_count")
+    incl = torch.cumsum(counts, 0, dtype=torch.int64)
+    offs = (incl - counts).contiguous()
+    n = int(incl[-1].item())                       # the one host read-back: rows to allocate
+    coords = torch.empty((n, 4), dtype=torch.int32, device=t.device)
+    feats = torch.empty((n, 1), dtype=torch.float32, device=t.device)
+    if n:
+        L.check(lib.scn_larcv_compact(t.data_ptr(), B, P, V, ncol, float(PAD_VALUE), offs.data_ptr(), layout,
+                                      coords.data_ptr(), feats.data_ptr(), L.stream()), "scn_larcv_compact")
+    return coords, feats, B
+
+
+def larcvsparse_to_scnsparse_3d_gpu(input_array):
+    """Device twin of :func:`larcvsparse_to_scnsparse_3d`: CUDA tensor ``[B, 1, MaxVoxels, 4]`` -> (coords int32
+    [N,4] = (x,y,z,batch), features [N,1], B), rows in the same (batch, voxel) order."""
+    coords, feats, b = _larcv_to_scn_gpu(input_array, 0)
+    return (coords, feats, b,)
+
+
+def larcvsparse_to_scnsparse_2d_gpu(input_array):
+    """Device twin of :func:`larcvsparse_to_scnsparse_2d`: ``[B, planes, MaxVoxels, 3]`` -> [coords int32 [N,4] =
+    (plane,y,x,batch), features [N,1], B], rows plane-major like the reference."""
+    coords, feats, b = _larcv_to_scn_gpu(input_array, 1)
+    return [coords, feats, b]

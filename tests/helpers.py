@@ -78,3 +78,23 @@ def small_batch(dataset, batch=2, seed=4321, max_voxels=6000):
     if dataset == "dune3d":
         return larcvsparse_to_scnsparse_3d(synthetic.larcv_batch_3d(batch, seed=seed, max_voxels=max_voxels))
     return larcvsparse_to_scnsparse_2d(synthetic.larcv_batch_2d(batch, seed=seed, max_voxels=max_voxels))
+
+
+# Legacy networks: reduced-depth instances of the reference's torch/sparseresnet3d.py and
+# torch/sparseresnet.py used for the committed fixtures (tests/golden/make_golden_legacy.py).
+LEGACY_CASES = {
+    "legacy3d_nf32_d2": {"kind": "3d", "cfg": dict(n_initial_filters=32, network_depth=2, depth_pre_merge=0,
+                                                   res_blocks_per_layer=1, batch_norm=True, leaky_relu=False)},
+    "legacy2d_nf32_d3_pre2": {"kind": "2d", "cfg": dict(n_initial_filters=32, network_depth=3, depth_pre_merge=2,
+                                                        res_blocks_per_layer=1, batch_norm=True, leaky_relu=True)},
+}
+
+
+def legacy_batch(case, batch=2, seed=2468, max_voxels=3000):
+    """The seeded synthetic mini-batch of a legacy fixture: SCN input tuple on the legacy grids."""
+    from sparseeventid_b200 import synthetic
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
+    if LEGACY_CASES[case]["kind"] == "3d":
+        return larcvsparse_to_scnsparse_3d(
+            synthetic.larcv_batch_3d(batch, seed=seed, grid=(1536, 1536, 1536), max_voxels=max_voxels))
+    return larcvsparse_to_scnsparse_2d(synthetic.larcv_batch_2d(batch, seed=seed, max_voxels=max_voxels))

@@ -390,3 +390,30 @@ def test_direct_gradient_accumulation_matches_autograd(scn, mode):
             assert float((ga - gb).abs().max()) <= 2e-4 * scale + 1e-6, (mode, rounds, n)
     assert arena.flat.abs().sum() > 0
     scn.set_precision("bf16")
+
+
+@pytest.mark.parametrize("dataset", ["dune3d", "dune2d"])
+def test_device_input_transform_matches_host_transform(scn, dataset):
+    """the device-side larcv -> SCN tuple (order-preserving compaction of the -999-padded batch filler
+    array) gives the same rows, in the same order, as the reference's numpy transform; InputLayer row numbering and
+    features downstream are therefore identical."""
+    from sparseeventid_b200 import data_transforms as T
+    from sparseeventid_b200 import synthetic
+    if dataset == "dune3d":
+        arr = synthetic.larcv_batch_3d(5, seed=11)
+        arr[2, 0, :, 3] = T.PAD_VALUE                  # an empty event
+        ch, fh, bh = T.larcvsparse_to_scnsparse_3d(arr)
+        cg, fg, bg = T.larcvsparse_to_scnsparse_3d_gpu(torch.from_numpy(arr).cuda())
+        grid = list(synthetic.GRID_3D)
+    else:
+        arr = synthetic.larcv_batch_2d(4, seed=12)
+        ch, fh, bh = T.larcvsparse_to_scnsparse_2d(arr)
+        cg, fg, bg = T.larcvsparse_to_scnsparse_2d_gpu(torch.from_numpy(arr).cuda())
+        grid = list(synthetic.GRID_2D)
+    assert bg == bh
+    assert np.array_equal(cg.cpu().numpy().astype(np.int64), np.asarray(ch).astype(np.int64))
+    assert np.array_equal(fg.cpu().numpy(), np.asarray(fh, dtype=np.float32))
+    xa = scn.InputLayer(3, grid)((torch.as_tensor(np.asarray(ch)).cuda(), torch.as_tensor(np.asarray(fh)).float().cuda(), bh))
+    xb = scn.InputLayer(3, grid)((cg, fg, bg))
+    assert torch.equal(xa.metadata.row_of_input, xb.metadata.row_of_input)
+    assert torch.equal(xa.features, xb.features)
