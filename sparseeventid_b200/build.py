@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = [o for o, _ in results]
     changed = any(c for _, c in results)
     if changed or not os.path.exists(LIB):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs
+        cmd = [NVCC] + ARCH + ["-shared", "-Xlinker", "-soname=libscn_b200.so", "-o", LIB] + objs
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -68,5 +68,29 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+TORCH_EXT_NAME = "scn_b200_torch"
+TORCH_EXT_DIR = os.path.join(HERE, "build_torch")
+TORCH_EXT_SO = os.path.join(TORCH_EXT_DIR, TORCH_EXT_NAME + ".so")
+
+
+def build_torch_ext(verbose: bool = False) -> str:
+    """In-tree build of the thin PyTorch C++ layer (csrc_torch/scn_torch.cpp -> build_torch/scn_b200_torch.so).
+    Host C++ only: the kernels stay in libscn_b200.so, which the loader (scn/_ext.py) maps first."""
+    import ctypes
+
+    from torch.utils import cpp_extension
+    # the extension NEEDs libscn_b200.so by soname: have it loaded (globally) before the import at the end of load()
+    ctypes.CDLL(build(), mode=ctypes.RTLD_GLOBAL)
+    os.makedirs(TORCH_EXT_DIR, exist_ok=True)
+    cpp_extension.load(
+        name=TORCH_EXT_NAME, sources=[os.path.join(HERE, "csrc_torch", "scn_torch.cpp")],
+        extra_cflags=["-O2", "-std=c++17"], extra_include_paths=["/usr/local/cuda/include"],
+        extra_ldflags=[f"-L{LIB_DIR}", "-lscn_b200", "-L/usr/local/cuda/lib64", "-lcudart"],
+        build_directory=TORCH_EXT_DIR, verbose=verbose, is_python_module=True, with_cuda=True)
+    return TORCH_EXT_SO
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--torch" in sys.argv:
+        print(build_torch_ext(verbose=True))

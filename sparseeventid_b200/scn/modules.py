@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from . import config, dense_view, ops
+from . import _ext, config, dense_view, ops
 from . import functional as F
 from .core import Metadata, Pending, SparseConvNetTensor, as_tuple
 
@@ -121,6 +121,29 @@ class _ConvBase(nn.Module):
             ws = table[key] = F.ConvWorkspace(K, cin, cout, prec, dtype, device)
         return ws
 
+    def _conv(self, x, nbr_fwd, nbr_bwd, n_out_rows, mirror):
+        """out = bias + conv(x): the C++ autograd function when the torch extension is built (one native call per
+        forward / backward), else functional.ConvFn (same kernels, more interpreter time)."""
+        ext = _ext.get()
+        w, b = self.weight, self.bias
+        if (ext is not None and x.is_cuda and not ops.profiling() and w.dtype == torch.float32 and w.is_contiguous()
+                and (b is None or (b.dtype == torch.float32 and b.is_contiguous()))):
+            prec, fdt = config.precision_code(), config.feature_dtype()
+            K, cin, cout = w.shape[0], w.shape[-2], w.shape[-1]
+            ws = self.workspace(K, cin, cout, prec, fdt, x.device)
+            if ws.path > 0 and x.dtype != fdt:
+                x = ops.convert(x, fdt)
+            key = (w._version, w.data_ptr())
+            skip = ws.fwd_key == key
+            ws.fwd_key = key
+            wimg_t = None
+            if x.requires_grad and torch.is_grad_enabled():
+                wimg_t = ws.bwd_buffer(K, cin, cout, prec, x.dtype, x.device)
+            return ext.conv(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, prec, L.SCN_BF16 if fdt == torch.bfloat16
+                            else L.SCN_F32, ws.fwd, wimg_t, skip, getattr(w, "_scn_direct_grad", False),
+                            b is not None and getattr(b, "_scn_direct_grad", False))
+        return F.ConvFn.apply(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, self)
+
     def _check(self, input):
         assert input.features.nelement() == 0 or input.features.size(1) == self.nIn, \
             f"expected {self.nIn} input planes, got {input.features.size(1)}"
@@ -144,7 +167,7 @@ class SubmanifoldConvolution(_ConvBase):
         md = input.metadata
         nbr = md.subm_table(input._sp(), self.filter_size)
         n = md.levels[input._sp()].n
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, nbr, nbr, n, True, self)
+        feats = self._conv(input.features, nbr, nbr, n, True)
         return _new_like(input, feats)
 
     def __repr__(self):
@@ -168,7 +191,7 @@ class Convolution(_ConvBase):
         self._check(input)
         md = input.metadata
         rule = md.strided_rule(input._sp(), self.filter_size, self.filter_stride)
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.down, rule.up, rule.n_out, False, self)
+        feats = self._conv(input.features, rule.down, rule.up, rule.n_out, False)
         return _new_like(input, feats, torch.LongTensor(list(rule.out_spatial)))
 
     def __repr__(self):
@@ -197,7 +220,7 @@ class Deconvolution(_ConvBase):
         if fine not in md.levels:
             raise RuntimeError("Deconvolution needs the fine grid to exist in the metadata")
         rule = md.strided_rule(fine, self.filter_size, self.filter_stride)
-        feats = F.ConvFn.apply(input.features, self.weight, self.bias, rule.up, rule.down, rule.n_in, False, self)
+        feats = self._conv(input.features, rule.up, rule.down, rule.n_in, False)
         return _new_like(input, feats, torch.LongTensor(list(fine)))
 
 
@@ -224,7 +247,16 @@ class BatchNormalization(nn.Module):
         training = self.training
 
         def run(leak=float(self.leakiness)):
-            return F.BatchNormFn.apply(x, self.weight, self.bias, self.running_mean, self.running_var, training,
+            ext = _ext.get()
+            w, b = self.weight, self.bias
+            if (ext is not None and x.is_cuda and not ops.profiling()
+                    and (w is None or (w.dtype == torch.float32 and w.is_contiguous() and b.dtype == torch.float32
+                                       and b.is_contiguous()))):
+                return ext.batch_norm(x, w, b, self.running_mean, self.running_var, training, float(self.eps),
+                                      float(self.momentum), leak,
+                                      w is not None and getattr(w, "_scn_direct_grad", False)
+                                      and getattr(b, "_scn_direct_grad", False))
+            return F.BatchNormFn.apply(x, w, b, self.running_mean, self.running_var, training,
                                        float(self.eps), float(self.momentum), leak)
         if config.fusion_enabled() and float(self.leakiness) == 1.0:
             # defer by one module: a following LeakyReLU/ReLU becomes the fused leakiness of this same kernel
@@ -257,7 +289,11 @@ class LeakyReLU(nn.Module):
         pend = input.take_pending() if isinstance(input, SparseConvNetTensor) else None
         if pend is not None:
             return _new_like(input, pend.fuse(float(self.leak)))
-        return _new_like(input, F.LeakyReLUFn.apply(input.features, float(self.leak)))
+        ext = _ext.get()
+        x = input.features
+        if ext is not None and x.is_cuda and not ops.profiling():
+            return _new_like(input, ext.leaky(x, float(self.leak)))
+        return _new_like(input, F.LeakyReLUFn.apply(x, float(self.leak)))
 
 
 class ReLU(LeakyReLU):
@@ -291,6 +327,9 @@ class AddTable(nn.Module):
                 return F.AddFn.apply(a, b)
 
             def fuse(leak):
+                ext = _ext.get()
+                if ext is not None and a.is_cuda and not ops.profiling():
+                    return ext.add_leaky(a, b, leak)
                 return F.AddLeakyFn.apply(a, b, leak)
             return SparseConvNetTensor(None, input[0].metadata, input[0].spatial_size, Pending("add", run, fuse),
                                        input[0]._spc)

@@ -52,13 +52,20 @@ class FlatGradArena:
         # BatchNorm / bias column sums) straight into the arena: no dW temporaries, no zero fills, no AccumulateGrad
         # adds (218 small launches per step).  Those never reach autograd's accumulation hook, so the functions call
         # `_scn_grad_ready` themselves; every other parameter (the dense heads) uses the normal hook.
+        self._param_of_ptr = {}
         for p in self.params:
             if getattr(p, "_scn_param", False):
                 p._scn_direct_grad = True
                 if self.world > 1:
                     p._scn_grad_ready = self._on_grad
+                    self._param_of_ptr[p.data_ptr()] = p
             elif self.world > 1:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+        if self.world > 1:
+            from .scn import _ext
+            ext = _ext.get()
+            if ext is not None:      # the C++ autograd functions report completed in-place gradients through this
+                ext.set_grad_ready_callback(lambda t: self._on_grad(self._param_of_ptr[t.data_ptr()]))
 
     def zero(self):
         self.flat.zero_()

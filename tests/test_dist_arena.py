@@ -43,7 +43,8 @@ def _worker(rank, world, port, q):
         arena.zero()
         model(x).pow(2).sum().backward()
         arena.finish()
-    q.put((rank, [p.grad.clone() for p in model.parameters()], [p.data.clone() for p in model.parameters()]))
+    # numpy (pickled by value): tensors would travel by file descriptor and need this process alive at receive time
+    q.put((rank, [p.grad.clone().numpy() for p in model.parameters()], [p.data.clone().numpy() for p in model.parameters()]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -58,7 +59,7 @@ def test_flat_arena_allreduce_mean_world2():
     res = {}
     for _ in range(world):
         r, grads, params = q.get(timeout=120)
-        res[r] = (grads, params)
+        res[r] = ([torch.from_numpy(g) for g in grads], [torch.from_numpy(v) for v in params])
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
