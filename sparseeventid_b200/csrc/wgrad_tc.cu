@@ -1,0 +1,366 @@
+// Weight gradient of the sparse convolutions on 5th-generation tensor cores (sm_100a only):
+//     dW[k] (+)= sum over pairs (i, o) of rules[k]   x[i, :]^T . dout[o, :]          (bf16 operands, fp32 accumulate)
+//
+// The contraction index is the PAIR, so -- unlike the forward, where missing neighbours are masked output rows -- the
+// live pairs of an offset can be compacted freely: a stage is 64 compacted pairs, its A operand the 64 gathered x rows
+// and its B operand the 64 gathered dout rows, both stored exactly like the forward's A tiles (one 128-byte row per
+// pair and 64-channel block, SWIZZLE_128B).  Read through MN-MAJOR shared-memory descriptors the same bytes are
+// x^T (M = input channels, K = pairs) and dout (K = pairs, N = output channels), so one tcgen05.mma (M=128, N=Cout,
+// K=16) contracts 16 pairs and the Cin x Cout accumulator of the offset stays in TMEM for the whole CTA.
+//
+// Work split: every CTA owns ONE offset k and a contiguous range of output rows (the centre offset of a submanifold
+// table holds every row and gets proportionally more CTAs), so dW receives one pass of atomics per CTA.
+// Roles: producer warps (each walks its share of 128-row blocks, ballots the neighbour indices, appends the live pairs
+// to a ring and emits a stage whenever 64 are pending; LDGSTS copies that signal their own landing), one issuing warp
+// that consumes whichever producer has a stage ready (order is irrelevant for a sum), 4 epilogue warps
+// (tcgen05.ld -> red.global.add.f32).
+//
+// Replaces SCN's dConvolution_KMxKN_backward_dW_A/B; reference call sites
+// src/networks/sparse_building_blocks.py:29-34,110-117 (backward).
+#include <cstdlib>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace wg {
+
+using namespace tcptx;
+
+constexpr int PAIRS = 64;                 // pairs (MMA K rows) per stage
+constexpr int BLK_BYTES = PAIRS * 128;    // one 64-channel block of a stage: 64 rows x 128 B
+constexpr int EPI_WARPS = 4;              // warps 0..3 (TMEM lane quarter = warp index)
+constexpr int PROD_WARPS = 6;             // warps 4..9; the first NPW are active, two slots each
+constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS;
+constexpr int THREADS = 32 * (WARP_MMA + 1);
+constexpr int MAX_SLOTS = 2 * PROD_WARPS;
+constexpr int RING = 256;                 // pending-pair ring per producer warp (entries), a power of two
+
+struct Params {
+  const __nv_bfloat16* x;       // [n_in_rows, Cin]
+  const __nv_bfloat16* dout;    // [n_rows, Cout]
+  const int32_t* nbr;           // [K][n_pad]: input row of output row o at offset k, or -1
+  float* dW;                    // [K][Cin][Cout], accumulated into
+  int64_t n_rows, n_pad;
+  int K, Cin, Cout;
+  int nca, ncb;                 // 64-channel blocks per stage: A (even: M = 128 reads two), B
+  int nmb;                      // M blocks of 128 input channels
+  int slots, npw;               // stage slots, active producer warps (slots == 2 * npw)
+  int s_other, s_centre, centre;   // CTAs per ordinary offset / for the centre offset (or -1)
+};
+
+// MN-major SWIZZLE_128B descriptor: rows of 128 bytes (64 elements along M/N), 8 K-rows per 1024-byte atom (SBO),
+// `lbo` bytes between consecutive 64-element blocks along M/N.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;       // descriptor version 1 (sm_100)
+  d |= (uint64_t)2 << 61;       // LayoutType::SWIZZLE_128B
+  return d;
+}
+// kind::f16, bf16 x bf16 -> fp32, A and B MN-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | (8u << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// NA / NB: 64-channel blocks of a stage's A (x rows) / B (dout rows) operand = ceil(Cin / 64), ceil(Cout / 64)
+template <int NA, int NB>
+__global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  unsigned char* gbase = smem_raw + (base - raw);
+  const int slots = p.slots, NPW = p.npw;
+  constexpr uint32_t slot_bytes = (uint32_t)(NA + NB) * BLK_BYTES;
+  const uint32_t bar0 = base + (uint32_t)slots * slot_bytes;
+  auto afull = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto aempty = [&](int s) { return bar0 + 8u * (uint32_t)(MAX_SLOTS + s); };
+  const uint32_t accf = bar0 + 8u * (uint32_t)(2 * MAX_SLOTS);
+  unsigned char* tail = gbase + (size_t)slots * slot_bytes + 8 * (2 * MAX_SLOTS + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
+  const uint32_t seq = smem_u32(tail + 16);                          // [MAX_SLOTS] u32: per-warp stage number + 1 (| parity << 31)
+  const uint32_t done = smem_u32(tail + 16 + 4 * MAX_SLOTS);         // [PROD_WARPS] u32: stages emitted + 1 once the warp is finished
+  int2* rings = reinterpret_cast<int2*>(tail + 16 + 4 * MAX_SLOTS + 4 * PROD_WARPS + 8);   // [PROD_WARPS][RING]
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  // ---- this CTA's offset and row range ------------------------------------------------------------------
+  int k, piece, pieces;
+  {
+    const int b = (int)blockIdx.x;
+    const int before = p.centre >= 0 ? p.centre * p.s_other : 0x7fffffff;
+    if (b < before) { k = b / p.s_other; piece = b % p.s_other; pieces = p.s_other; }
+    else if (b < before + p.s_centre) { k = p.centre; piece = b - before; pieces = p.s_centre; }
+    else { const int b2 = b - p.s_centre + p.s_other; k = b2 / p.s_other; piece = b2 % p.s_other; pieces = p.s_other; }
+  }
+  const int64_t nblocks = (p.n_rows + 127) / 128;                    // 128-row blocks of the table
+  const int64_t blk_lo = nblocks * piece / pieces, blk_hi = nblocks * (piece + 1) / pieces;
+
+  if (warp == WARP_MMA) {
+    if (lane == 0) {
+      for (int s = 0; s < slots; ++s) {
+        st_release_u32(seq + 4u * (uint32_t)s, 0u);
+        mbar_init(afull(s), 32);                 // the 32 lanes of the owning producer warp, each when its copies landed
+        mbar_init(aempty(s), 1);                 // one tcgen05.commit
+      }
+      for (int w = 0; w < PROD_WARPS; ++w) st_release_u32(done + 4u * (uint32_t)w, 0u);
+      mbar_init(accf, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
+    // ================================ producers =============================================
+    const int pw = warp - EPI_WARPS;
+    if (pw < NPW) {
+      int2* ring = rings + pw * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
+      const uint32_t xvec = (uint32_t)p.Cin >> 3, dvec = (uint32_t)p.Cout >> 3;
+      const uint32_t lt = (1u << lane) - 1u;
+      const int chunk = lane & 7, sub = lane >> 3;
+      const uint32_t csw = (uint32_t)chunk << 4;
+      const unsigned char* xb = reinterpret_cast<const unsigned char*>(p.x);
+      const unsigned char* db = reinterpret_cast<const unsigned char*>(p.dout);
+      int head = 0, pending = 0, emitted = 0;
+
+      // per-lane invariants of the copies: this lane moves 16-byte chunk `chunk` of every 64-channel block
+      bool a_ok[NA], b_ok[NB];
+#pragma unroll
+      for (int b = 0; b < NA; ++b) a_ok[b] = b * 64 + chunk * 8 < p.Cin;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) b_ok[b] = b * 64 + chunk * 8 < p.Cout;
+      const unsigned char* xsrc = xb + ((uint32_t)chunk << 4);
+      const unsigned char* dsrc = db + ((uint32_t)chunk << 4);
+
+      // emits one stage from the first `take` (<= 64) pending pairs; rows beyond `take` are zero-filled.
+      // ~6 instructions per 16-byte copy: LDS.64 (shared by the row's copies), IMAD.WIDE, LOP3, LDGSTS.
+      auto emit = [&](int take) {
+        const int slot = pw + (emitted & 1) * NPW;
+        const uint32_t sbase = base + (uint32_t)slot * slot_bytes;
+        mbar_wait(aempty(slot), (((uint32_t)emitted >> 1) & 1u) ^ 1u);   // MMAs of this slot's previous stage retired
+#pragma unroll 4
+        for (int pass = 0; pass < PAIRS / 4; ++pass) {
+          const int row = pass * 4 + sub;                    // stage row (pair), 8 lanes per row
+          const bool live = row < take;
+          const int2 e = live ? ring[(head + row) & (RING - 1)] : make_int2(0, 0);
+          const uint32_t dst = (sbase + (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4)) ^ csw;
+          const unsigned char* xs = xsrc + ((uint64_t)(uint32_t)e.x << 4);
+          const unsigned char* ds = dsrc + ((uint64_t)(uint32_t)e.y << 4);
+#pragma unroll
+          for (int b = 0; b < NA; ++b) {                     // x row -> A blocks
+            const bool ok = live && a_ok[b];
+            cp_async16(dst + (uint32_t)b * BLK_BYTES, ok ? xs + b * 128 : xs, ok ? 16u : 0u);
+          }
+#pragma unroll
+          for (int b = 0; b < NB; ++b) {                     // dout row -> B blocks
+            const bool ok = live && b_ok[b];
+            cp_async16(dst + (uint32_t)(NA + b) * BLK_BYTES, ok ? ds + b * 128 : ds, ok ? 16u : 0u);
+          }
+        }
+        cp_async_arrive_noinc(afull(slot));
+        __syncwarp();
+        if (lane == 0)
+          st_release_u32(seq + 4u * (uint32_t)slot, ((uint32_t)emitted + 1u) | ((((uint32_t)emitted >> 1) & 1u) << 31));
+        head = (head + take) & (RING - 1);
+        pending -= take;
+        ++emitted;
+      };
+
+      const int32_t* tab = p.nbr + (int64_t)k * p.n_pad;
+      for (int64_t blk = blk_lo + pw; blk < blk_hi; blk += NPW) {
+        const int64_t o0 = blk * 128;
+        int j[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) j[i] = ldg_nc32(tab + o0 + 32 * i + lane);   // table rows beyond n_rows are -1 padding
+        int at = pending;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t m = __ballot_sync(0xffffffffu, j[i] >= 0);
+          if (j[i] >= 0)
+            ring[(head + at + __popc(m & lt)) & (RING - 1)] =
+                make_int2((int)((uint32_t)j[i] * xvec), (int)((uint32_t)(o0 + 32 * i + lane) * dvec));
+          at += __popc(m);
+        }
+        pending = at;
+        __syncwarp();
+        while (pending >= PAIRS) emit(PAIRS);
+      }
+      if (pending > 0) emit(pending);
+      if (lane == 0) st_release_u32(done + 4u * (uint32_t)pw, (uint32_t)emitted + 1u);
+    }
+  } else if (warp == WARP_MMA) {
+    // ================================ MMA issuer ============================================
+    const uint32_t idesc = make_idesc_mn(p.Cout);
+    const uint32_t a_lbo = BLK_BYTES, b_lbo = BLK_BYTES;
+    int consumed[PROD_WARPS];
+#pragma unroll
+    for (int w = 0; w < PROD_WARPS; ++w) consumed[w] = 0;
+    bool first = true;
+    uint32_t idle = 0;
+    for (;;) {
+      bool all_done = true, progressed = false;
+#pragma unroll
+      for (int w = 0; w < PROD_WARPS; ++w) {
+        if (w >= NPW) continue;
+        // one lane's view of the flags, broadcast: the branch below must be warp-uniform
+        const uint32_t dn = __shfl_sync(0xffffffffu, ld_acquire_u32(done + 4u * (uint32_t)w), 0);
+        if (dn != 0u && (uint32_t)consumed[w] + 1u == dn) continue;           // this warp is finished and drained
+        all_done = false;
+        const int slot = w + (consumed[w] & 1) * NPW;
+        const uint32_t f = __shfl_sync(0xffffffffu, ld_acquire_u32(seq + 4u * (uint32_t)slot), 0);
+        if ((f & 0x7fffffffu) != (uint32_t)consumed[w] + 1u) continue;         // its next stage is not issued yet
+        __syncwarp();
+        mbar_wait(afull(slot), f >> 31);                                       // ... and landed
+        tc_fence_after();
+        const uint32_t sbase = base + (uint32_t)slot * slot_bytes;
+        if (elect_one()) {
+#pragma unroll
+          for (int mb = 0; mb < (NA + 1) / 2; ++mb) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(mb * p.Cout);
+            // M = 128 reads two 64-channel blocks; an odd last block is read twice (LBO = 0): accumulator rows
+            // 64..127 of that M block are then copies the epilogue never looks at
+            const uint32_t lbo = (2 * mb + 1 < NA) ? a_lbo : 0u;
+#pragma unroll
+            for (int kk = 0; kk < PAIRS / 16; ++kk) {
+              const uint64_t da = make_desc_mn_sw128(sbase + (uint32_t)(2 * mb) * BLK_BYTES + (uint32_t)kk * 2048u, lbo);
+              const uint64_t db = make_desc_mn_sw128(sbase + (uint32_t)NA * BLK_BYTES + (uint32_t)kk * 2048u, b_lbo);
+              umma(tmem_d, da, db, idesc, (first && kk == 0) ? 0u : 1u);
+            }
+          }
+          umma_commit(aempty(slot));
+        }
+        __syncwarp();
+        first = false;
+        ++consumed[w];
+        progressed = true;
+      }
+      if (all_done) break;
+      if (!progressed && ++idle > SPIN_LIMIT) __trap();
+      if (progressed) idle = 0;
+    }
+    // `first` still true <=> no pair at all in this CTA's range: the epilogue must not add the (uninitialised) accumulator.
+    // Written before the commit: the epilogue reads it after the commit's barrier has completed.
+    if (lane == 0) st_release_u32(done + 4u * (uint32_t)PROD_WARPS, first ? 1u : 2u);
+    __syncwarp();
+    if (elect_one()) umma_commit(accf);
+    __syncwarp();
+  } else if (warp < EPI_WARPS) {
+    // ================================ epilogue: TMEM -> dW atomics ============================
+    mbar_wait_sleep(accf, 0u);
+    tc_fence_after();
+    const uint32_t any = ld_acquire_u32(done + 4u * (uint32_t)PROD_WARPS);
+    if (any == 2u) {
+      for (int mb = 0; mb < (NA + 1) / 2; ++mb) {
+        const int cin = mb * 128 + warp * 32 + lane;                            // accumulator row == input channel
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * p.Cout);
+        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + (uint32_t)c0, v);
+          if (cin < p.Cin) {
+            float* dst = p.dW + ((int64_t)k * p.Cin + cin) * p.Cout + c0;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float f = __uint_as_float(v[e]);
+              if (f != 0.f) atomicAdd(dst + e, f);
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+}  // namespace wg
+
+bool scn_wgrad_tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SCN_B200_WGRAD_TC");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+// dW[K][Cin][Cout] += ...; x, dout bf16.  Returns SCN_ERR_UNSUPPORTED for shapes outside the kernel (caller falls back).
+int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16* dout, const int32_t* nbr, int K,
+                 int64_t n_rows, int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s) {
+  if ((Cin % 32) || (Cout % 32) || Cin < 32 || Cout < 32 || Cin > 256 || Cout > 256 || K < 1) return SCN_ERR_UNSUPPORTED;
+  if ((uint64_t)n_in_rows * (uint64_t)(Cin >> 3) >= 0xffffffffull || (uint64_t)n_rows * (uint64_t)(Cout >> 3) >= 0xffffffffull)
+    return SCN_ERR_UNSUPPORTED;
+  if (n_pad < ((n_rows + 127) / 128) * 128) return SCN_ERR_ARG;      // whole 128-row blocks are read
+  wg::Params p;
+  p.x = x; p.dout = dout; p.nbr = nbr; p.dW = dW; p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.Cin = Cin; p.Cout = Cout;
+  p.nmb = (Cin + 127) / 128;
+  p.nca = (Cin + 63) / 64;
+  p.ncb = (Cout + 63) / 64;
+  if (p.nmb * Cout > 512) return SCN_ERR_UNSUPPORTED;
+  const uint32_t slot_bytes = (uint32_t)(p.nca + p.ncb) * wg::BLK_BYTES;
+  const uint32_t fixed = 1024u + 8u * (2 * wg::MAX_SLOTS + 2) + 16u + 4u * wg::MAX_SLOTS + 4u * wg::PROD_WARPS + 8u +
+                         (uint32_t)wg::PROD_WARPS * wg::RING * 8u;
+  int slots = (int)((226u * 1024u - fixed) / slot_bytes);
+  if (slots > wg::MAX_SLOTS) slots = wg::MAX_SLOTS;
+  slots &= ~1;
+  if (slots < 2) return SCN_ERR_UNSUPPORTED;
+  p.slots = slots;
+  p.npw = slots / 2;
+  // CTAs: two full waves (one CTA per SM at a time); the centre offset of an odd-sized (submanifold) table holds
+  // every row -> 3.5x the share.  Rounded DOWN so that the grid never spills into a third, nearly empty wave.
+  const int target = 2 * kNumSMs;
+  const int64_t nblocks = (n_rows + 127) / 128;
+  if ((K & 1) && K > 1) {
+    p.centre = K / 2;
+    const double unit = (double)target / ((double)(K - 1) + 3.5);
+    p.s_other = (int)unit;
+    if (p.s_other < 1) p.s_other = 1;
+    p.s_centre = target - (K - 1) * p.s_other;
+  } else {
+    p.centre = -1;
+    p.s_other = target / K;
+    p.s_centre = 0;
+  }
+  if (p.s_other < 1) p.s_other = 1;
+  if (p.s_other > nblocks) p.s_other = (int)(nblocks > 0 ? nblocks : 1);
+  if (p.centre >= 0) {
+    if (p.s_centre < 1) p.s_centre = 1;
+    if (p.s_centre > nblocks) p.s_centre = (int)(nblocks > 0 ? nblocks : 1);
+  }
+  const int grid = (p.centre >= 0 ? (K - 1) * p.s_other + p.s_centre : K * p.s_other);
+  const size_t smem = (size_t)fixed + (size_t)slots * slot_bytes;
+  auto launch = [&](auto kern) -> int {
+    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, wg::THREADS, smem, s>>>(p);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  };
+#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b>)
+  WG_CASE(1, 1); WG_CASE(1, 2); WG_CASE(1, 3); WG_CASE(1, 4);
+  WG_CASE(2, 1); WG_CASE(2, 2); WG_CASE(2, 3); WG_CASE(2, 4);
+  WG_CASE(3, 1); WG_CASE(3, 2); WG_CASE(3, 3); WG_CASE(3, 4);
+  WG_CASE(4, 1); WG_CASE(4, 2); WG_CASE(4, 3); WG_CASE(4, 4);
+#undef WG_CASE
+  return SCN_ERR_UNSUPPORTED;
+}

@@ -88,16 +88,17 @@ def one_case(coords, grid, C, peaks, label):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--full", action="store_true", help="the whole SURVEY grid (C 16..256, N up to 1e7)")
+    ap.add_argument("--tracks-only", action="store_true", help="only the track-like case of every channel count")
     ap.add_argument("--out", default=os.path.join("gpurun_out", "conv_sweep.json"))
     a = ap.parse_args()
     scn.set_precision("bf16")
     peaks = load_peaks()
-    chans = [16, 32, 64, 128, 256] if a.full else [32, 64, 128, 256]
+    chans = [16, 32, 64, 128, 256] if a.full else ([32, 64, 96, 128, 160, 192] if a.tracks_only else [32, 64, 128, 256])
     sizes = [10_000, 100_000, 1_000_000, 10_000_000] if a.full else [10_000, 100_000, 1_000_000]
     occs = [0.001, 0.01, 0.05]
     out = []
     for C in chans:
-        for n in sizes:
+        for n in ([] if a.tracks_only else sizes):
             if n * C > 3_000_000_000 // 2:
                 continue
             for oi, occ in enumerate(occs):
