@@ -73,7 +73,8 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 }
 
 // NA / NB: 64-channel blocks of a stage's A (x rows) / B (dout rows) operand = ceil(Cin / 64), ceil(Cout / 64)
-template <int NA, int NB>
+// HALF: Cin == Cout == 32, rows are 64 bytes: 4 lanes per row and 8 rows per pass instead of 8 lanes / 4 rows
+template <int NA, int NB, bool HALF>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -133,7 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
       int2* ring = rings + pw * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
       const uint32_t xvec = (uint32_t)p.Cin >> 3, dvec = (uint32_t)p.Cout >> 3;
       const uint32_t lt = (1u << lane) - 1u;
-      const int chunk = lane & 7, sub = lane >> 3;
+      constexpr int LPR = HALF ? 4 : 8;                     // lanes per row
+      constexpr int RPP = 32 / LPR;                         // rows per pass
+      const int chunk = lane % LPR, sub = lane / LPR;
       const uint32_t csw = (uint32_t)chunk << 4;
       const unsigned char* xb = reinterpret_cast<const unsigned char*>(p.x);
       const unsigned char* db = reinterpret_cast<const unsigned char*>(p.dout);
@@ -155,8 +158,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
         const uint32_t sbase = base + (uint32_t)slot * slot_bytes;
         mbar_wait(aempty(slot), (((uint32_t)emitted >> 1) & 1u) ^ 1u);   // MMAs of this slot's previous stage retired
 #pragma unroll 4
-        for (int pass = 0; pass < PAIRS / 4; ++pass) {
-          const int row = pass * 4 + sub;                    // stage row (pair), 8 lanes per row
+        for (int pass = 0; pass < PAIRS / RPP; ++pass) {
+          const int row = pass * RPP + sub;                  // stage row (pair), LPR lanes per row
           const bool live = row < take;
           const int2 e = live ? ring[(head + row) & (RING - 1)] : make_int2(0, 0);
           const uint32_t dst = (sbase + (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4)) ^ csw;
@@ -183,11 +186,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
       };
 
       const int32_t* tab = p.nbr + (int64_t)k * p.n_pad;
+      int jn[4] = {-1, -1, -1, -1};                       // indices of the NEXT block, loaded one block ahead
+      if (blk_lo + pw < blk_hi) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) jn[i] = ldg_nc32(tab + (blk_lo + pw) * 128 + 32 * i + lane);
+      }
       for (int64_t blk = blk_lo + pw; blk < blk_hi; blk += NPW) {
         const int64_t o0 = blk * 128;
         int j[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) j[i] = ldg_nc32(tab + o0 + 32 * i + lane);   // table rows beyond n_rows are -1 padding
+        for (int i = 0; i < 4; ++i) j[i] = jn[i];          // (table rows beyond n_rows are -1 padding)
+        if (blk + NPW < blk_hi) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) jn[i] = ldg_nc32(tab + (blk + NPW) * 128 + 32 * i + lane);
+        }
         int at = pending;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -329,7 +341,13 @@ int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16*
   p.npw = slots / 2;
   // CTAs: two full waves (one CTA per SM at a time); the centre offset of an odd-sized (submanifold) table holds
   // every row -> 3.5x the share.  Rounded DOWN so that the grid never spills into a third, nearly empty wave.
-  const int target = 2 * kNumSMs;
+  // Small tables get fewer CTAs: every CTA pays a fixed price (TMEM allocation, Cin*Cout atomics), so it should own
+  // ~1000 pairs or more (about 30% of the K*n table entries are pairs in the reference's networks).
+  int target = 2 * kNumSMs;
+  {
+    const int64_t by_work = (int64_t)((double)n_rows * K * 0.3 / 1024.0);
+    if (by_work < target) target = (int)(by_work < K ? K : by_work);
+  }
   const int64_t nblocks = (n_rows + 127) / 128;
   if ((K & 1) && K > 1) {
     p.centre = K / 2;
@@ -337,6 +355,7 @@ int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16*
     p.s_other = (int)unit;
     if (p.s_other < 1) p.s_other = 1;
     p.s_centre = target - (K - 1) * p.s_other;
+    if (p.s_centre > (int)(3.5 * unit + 1.5)) p.s_centre = (int)(3.5 * unit + 1.5);
   } else {
     p.centre = -1;
     p.s_other = target / K;
@@ -356,7 +375,8 @@ int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16*
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };
-#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b>)
+  if (Cin == 32 && Cout == 32) return launch(wg::k_wgrad_tc<1, 1, true>);
+#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b, false>)
   WG_CASE(1, 1); WG_CASE(1, 2); WG_CASE(1, 3); WG_CASE(1, 4);
   WG_CASE(2, 1); WG_CASE(2, 2); WG_CASE(2, 3); WG_CASE(2, 4);
   WG_CASE(3, 1); WG_CASE(3, 2); WG_CASE(3, 3); WG_CASE(3, 4);
