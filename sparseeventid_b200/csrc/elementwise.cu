@@ -62,6 +62,35 @@ template <typename T> struct LoadVec<T, 4> {
   }
   static __device__ __forceinline__ void st(T* p, const float* o) { st4(p, make_float4(o[0], o[1], o[2], o[3])); }
 };
+// 8 consecutive elements: ONE 16-byte access for bf16 (two for fp32) -- twice the bytes in flight per thread
+template <> struct LoadVec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* o) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+      o[2 * i] = f.x;
+      o[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* o) {
+    uint4 u;
+    u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]);
+    u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct LoadVec<float, 8> {
+  static __device__ __forceinline__ void ld(const float* p, float* o) {
+    const float4 a = ld4(p), b = ld4(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+  static __device__ __forceinline__ void st(float* p, const float* o) {
+    st4(p, make_float4(o[0], o[1], o[2], o[3]));
+    st4(p + 4, make_float4(o[4], o[5], o[6], o[7]));
+  }
+};
 template <typename T> struct LoadVec<T, 1> {
   static __device__ __forceinline__ void ld(const T* p, float* o) { o[0] = Elem<T>::ld(p); }
   static __device__ __forceinline__ void st(T* p, const float* o) { Elem<T>::st(p, o[0]); }
@@ -305,11 +334,13 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
                  int training, float eps, float momentum, float leak, float* save_mean, float* save_invstd,
                  double* ws, T* out, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
+  const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
   if (training) {
     SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
     if (n > 0) {
-      int rc = vec ? launch_col_reduce<4>(StatsF<T, 4>{x, C}, n, C, ws, s)
-                   : launch_col_reduce<1>(StatsF<T, 1>{x, C}, n, C, ws, s);
+      int rc = vec8 ? launch_col_reduce<8>(StatsF<T, 8>{x, C}, n, C, ws, s)
+               : vec ? launch_col_reduce<4>(StatsF<T, 4>{x, C}, n, C, ws, s)
+                     : launch_col_reduce<1>(StatsF<T, 1>{x, C}, n, C, ws, s);
       if (rc) return rc;
     }
   }
@@ -318,7 +349,10 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
   SCN_LAUNCH_CHECK();
   if (n == 0) return SCN_OK;
   int64_t total = n * C;
-  if (vec)
+  if (vec8)
+    k_bn_apply<T, 8><<<grid_for(total / 8, 256), 256, 0, s>>>(x, total / 8, C, save_mean, save_invstd, gamma, beta,
+                                                              leak, out);
+  else if (vec)
     k_bn_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, total / 4, C, save_mean, save_invstd, gamma, beta,
                                                               leak, out);
   else
@@ -332,17 +366,22 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
                   const float* mean, const float* invstd, int training, float leak, double* ws, T* dx, float* dgamma,
                   float* dbeta, int accumulate, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
+  const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) & 15) == 0;
   SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
   if (n > 0) {
-    int rc = vec ? launch_col_reduce<4>(BnBwdF<T, 4>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s)
-                 : launch_col_reduce<1>(BnBwdF<T, 1>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s);
+    int rc = vec8 ? launch_col_reduce<8>(BnBwdF<T, 8>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s)
+             : vec ? launch_col_reduce<4>(BnBwdF<T, 4>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s)
+                   : launch_col_reduce<1>(BnBwdF<T, 1>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s);
     if (rc) return rc;
   }
   k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, accumulate);
   SCN_LAUNCH_CHECK();
   if (n == 0) return SCN_OK;
   int64_t total = n * C;
-  if (vec)
+  if (vec8)
+    k_bn_bwd_apply<T, 8><<<grid_for(total / 8, 256), 256, 0, s>>>(x, dout, total / 8, C, n, mean, invstd, gamma, beta,
+                                                                  leak, training, ws, dx);
+  else if (vec)
     k_bn_bwd_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, dout, total / 4, C, n, mean, invstd, gamma, beta,
                                                                   leak, training, ws, dx);
   else
@@ -363,6 +402,15 @@ template <typename T>
 int ew_launch3(int which, const T* a, const T* b, int64_t count, float leak, T* out, cudaStream_t s) {
   if (count == 0) return SCN_OK;
   bool vec = (count % 4 == 0) && ((((uintptr_t)a | (uintptr_t)b | (uintptr_t)out) & 15) == 0);
+  if (vec && count % 8 == 0) {                 // 16-byte accesses for bf16, 2 x 16 bytes for fp32
+    const int64_t n8 = count / 8;
+    const unsigned g8 = grid_for(n8, 256);
+    if (which == 0) k_leaky_fwd<T, 8><<<g8, 256, 0, s>>>(a, n8, leak, out);
+    else if (which == 1) k_leaky_bwd<T, 8><<<g8, 256, 0, s>>>(a, b, n8, leak, out);
+    else k_add_fwd<T, 8><<<g8, 256, 0, s>>>(a, b, n8, leak, out);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   int64_t nv = vec ? count / 4 : count;
   unsigned g = grid_for(nv, 256);
   if (which == 0) {
