@@ -182,6 +182,72 @@ __global__ void k_bn_apply(const T* __restrict__ x, int64_t nvec, int C, const f
   LoadVec<T, VEC>::st(out + i * VEC, v);
 }
 
+// Row-streaming forms of the two apply kernels (C % 8 == 0, C / 8 <= 256): a thread owns 8 fixed channels, folds
+// their per-channel coefficients into registers ONCE and then streams rows with 16-byte accesses.  (The
+// element-indexed forms above re-load 4-6 per-channel values for every element: LSU-bound at ~1.7 TB/s.)
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_apply_rows(const T* __restrict__ x, int64_t n, int C,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       float leak, T* __restrict__ out) {
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  if (ty >= RY) return;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tx * 8 + k;
+    sc[k] = invstd[c] * (gamma ? gamma[c] : 1.f);
+    sh[k] = (beta ? beta[c] : 0.f) - mean[c] * sc[k];
+  }
+  for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += (int64_t)gridDim.x * RY) {
+    float v[8];
+    LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      // same association as the element-indexed kernel: ((x - mean) * invstd) * gamma + beta, up to one rounding
+      const float y = fmaf(v[k], sc[k], sh[k]);
+      v[k] = (leak != 1.f && !(y > 0.f)) ? y * leak : y;
+    }
+    LoadVec<T, 8>::st(out + r * C + tx * 8, v);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_rows(const T* __restrict__ x, const T* __restrict__ dout, int64_t n,
+                                                           int C, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float leak, int training,
+                                                           const double* __restrict__ acc, T* __restrict__ dx) {
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  if (ty >= RY) return;
+  float m[8], is[8], g[8], b[8], s1[8], s2[8];
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tx * 8 + k;
+    m[k] = mean[c]; is[k] = invstd[c];
+    g[k] = gamma ? gamma[c] : 1.f;
+    b[k] = beta ? beta[c] : 0.f;
+    s1[k] = training ? (float)acc[c] * inv_n : 0.f;
+    s2[k] = training ? (float)acc[C + c] * inv_n : 0.f;
+  }
+  for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += (int64_t)gridDim.x * RY) {
+    float v[8], d[8];
+    LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+    LoadVec<T, 8>::ld(dout + r * C + tx * 8, d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xh = (v[k] - m[k]) * is[k];
+      const float y = xh * g[k] + b[k];
+      const float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+      v[k] = g[k] * is[k] * (dd - s1[k] - xh * s2[k]);
+    }
+    LoadVec<T, 8>::st(dx + r * C + tx * 8, v);
+  }
+}
+
 template <typename T, int VEC>
 __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dout, int64_t nvec, int C, int64_t n,
                                const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -349,10 +415,13 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
   SCN_LAUNCH_CHECK();
   if (n == 0) return SCN_OK;
   int64_t total = n * C;
-  if (vec8)
-    k_bn_apply<T, 8><<<grid_for(total / 8, 256), 256, 0, s>>>(x, total / 8, C, save_mean, save_invstd, gamma, beta,
-                                                              leak, out);
-  else if (vec)
+  if (vec8 && C <= 2048) {
+    const int ry = 256 / (C >> 3);
+    int64_t g = (n + (int64_t)ry * 4 - 1) / ((int64_t)ry * 4);      // >= 4 rows per thread
+    if (g > (int64_t)kNumSMs * 8) g = (int64_t)kNumSMs * 8;
+    if (g < 1) g = 1;
+    k_bn_apply_rows<T><<<(unsigned)g, 256, 0, s>>>(x, n, C, save_mean, save_invstd, gamma, beta, leak, out);
+  } else if (vec)
     k_bn_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, total / 4, C, save_mean, save_invstd, gamma, beta,
                                                               leak, out);
   else
@@ -378,10 +447,13 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
   SCN_LAUNCH_CHECK();
   if (n == 0) return SCN_OK;
   int64_t total = n * C;
-  if (vec8)
-    k_bn_bwd_apply<T, 8><<<grid_for(total / 8, 256), 256, 0, s>>>(x, dout, total / 8, C, n, mean, invstd, gamma, beta,
-                                                                  leak, training, ws, dx);
-  else if (vec)
+  if (vec8 && C <= 2048) {
+    const int ry = 256 / (C >> 3);
+    int64_t g = (n + (int64_t)ry * 4 - 1) / ((int64_t)ry * 4);
+    if (g > (int64_t)kNumSMs * 8) g = (int64_t)kNumSMs * 8;
+    if (g < 1) g = 1;
+    k_bn_bwd_apply_rows<T><<<(unsigned)g, 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, training, ws, dx);
+  } else if (vec)
     k_bn_bwd_apply<T, 4><<<grid_for(total / 4, 256), 256, 0, s>>>(x, dout, total / 4, C, n, mean, invstd, gamma, beta,
                                                                   leak, training, ws, dx);
   else
