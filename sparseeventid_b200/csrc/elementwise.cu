@@ -4,7 +4,16 @@
 // src/networks/sparse_building_blocks.py:39,45,80-82,96-98,122,128; src/networks/resnet.py:123-125,143).
 // All kernels are HBM-bound: 16-byte (fp32) / 8-byte (bf16) vector accesses along channels,
 // fp32 math, column reductions finished with fp64 atomics.
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -248,6 +257,215 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply_rows(const T* __restrict__
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training-mode BatchNormalization in ONE cooperative launch per direction (C % 8 == 0, C <= 2048).
+// The four-launch form (memset, column reduction, finalize, apply) costs ~27 us (forward) / ~40 us (backward) of
+// launch latency and dependency bubbles even on a 7 k-row level, more than the data movement of every level below
+// the first two.  Here: phase 1 = column sums (registers -> shared memory -> one fp64 atomic per channel and block),
+// grid.sync(), phase 2 = every thread folds the statistics of ITS 8 channels into registers and streams the rows
+// (the re-read of x comes from L2 for most levels), grid.sync(), and the accumulators are zeroed again for the next
+// user -- `acc` must be all zero on entry (scn_bn_*: the scratch is zero-initialised once and every kernel that uses
+// it leaves it zero).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_fwd_fused(const T* __restrict__ x, int64_t n, int C, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* running_mean,
+                                                      float* running_var, float eps, float momentum, float leak,
+                                                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                      double* acc, T* __restrict__ out) {
+  extern __shared__ float sred[];                        // [RY][CV][16]
+  cg::grid_group grid = cg::this_grid();
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const bool active = ty < RY;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  // ---- phase 1: sum and sum of squares of (x - pivot), pivot = row 0
+  float a[8], b[8], pv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (active) {
+    LoadVec<T, 8>::ld(x + tx * 8, pv);
+    for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += stride) {
+      float v[8];
+      LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[k] - pv[k]; a[k] += d; b[k] += d * d; }
+    }
+    float* dst = sred + ((size_t)ty * CV + tx) * 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dst[k] = a[k]; dst[8 + k] = b[k]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 16; i += 256) {
+    const int cx = i >> 4, w = i & 15;
+    float sum = 0.f;
+    for (int y = 0; y < RY; ++y) sum += sred[((size_t)y * CV + cx) * 16 + w];
+    atomicAdd(acc + (size_t)(w >> 3) * C + cx * 8 + (w & 7), (double)sum);
+  }
+  grid.sync();
+  // ---- phase 2: statistics of this thread's channels, running statistics (block 0), apply
+  float sc[8], sh[8];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = tx * 8 + k;
+      const double s1 = acc[c] / (double)n, s2 = acc[C + c] / (double)n;
+      const double mean = (double)pv[k] + s1;
+      double var = s2 - s1 * s1;
+      if (var < 0.0) var = 0.0;
+      const float m = (float)mean, is = (float)(1.0 / sqrt(var + (double)eps));
+      if (blockIdx.x == 0 && ty == 0) {
+        const double unbiased = var * (double)n / (double)(n > 1 ? n - 1 : 1);
+        running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
+        running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * unbiased);
+        save_mean[c] = m;
+        save_invstd[c] = is;
+      }
+      sc[k] = is * (gamma ? gamma[c] : 1.f);
+      sh[k] = (beta ? beta[c] : 0.f) - m * sc[k];
+    }
+    for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += stride) {
+      float v[8];
+      LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = fmaf(v[k], sc[k], sh[k]);
+        v[k] = (leak != 1.f && !(y > 0.f)) ? y * leak : y;
+      }
+      LoadVec<T, 8>::st(out + r * C + tx * 8, v);
+    }
+  }
+  grid.sync();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * C; i += 256) acc[i] = 0.0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_bn_bwd_fused(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
+                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                      float leak, double* acc, T* __restrict__ dx, float* dgamma,
+                                                      float* dbeta, int accumulate) {
+  extern __shared__ float sred[];
+  cg::grid_group grid = cg::this_grid();
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const bool active = ty < RY;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  float m[8], is[8], g[8], bt[8];
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = tx * 8 + k;
+      m[k] = mean[c]; is[k] = invstd[c];
+      g[k] = gamma ? gamma[c] : 1.f;
+      bt[k] = beta ? beta[c] : 0.f;
+    }
+  }
+  // ---- phase 1: sums of d and d * xhat  (d = dout through the fused leaky ReLU)
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (active) {
+    for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += stride) {
+      float v[8], d[8];
+      LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+      LoadVec<T, 8>::ld(dout + r * C + tx * 8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (v[k] - m[k]) * is[k];
+        const float y = xh * g[k] + bt[k];
+        const float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+        a[k] += dd;
+        b[k] += dd * xh;
+      }
+    }
+    float* dst = sred + ((size_t)ty * CV + tx) * 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { dst[k] = a[k]; dst[8 + k] = b[k]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 16; i += 256) {
+    const int cx = i >> 4, w = i & 15;
+    float sum = 0.f;
+    for (int y = 0; y < RY; ++y) sum += sred[((size_t)y * CV + cx) * 16 + w];
+    atomicAdd(acc + (size_t)(w >> 3) * C + cx * 8 + (w & 7), (double)sum);
+  }
+  grid.sync();
+  // ---- phase 2: parameter gradients (block 0), dx
+  if (active) {
+    float s1[8], s2[8];
+    const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = tx * 8 + k;
+      const double sa = acc[c], sb = acc[C + c];
+      if (blockIdx.x == 0 && ty == 0) {
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sa;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sb;
+      }
+      s1[k] = (float)sa * inv_n;
+      s2[k] = (float)sb * inv_n;
+    }
+    for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += stride) {
+      float v[8], d[8];
+      LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+      LoadVec<T, 8>::ld(dout + r * C + tx * 8, d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (v[k] - m[k]) * is[k];
+        const float y = xh * g[k] + bt[k];
+        const float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+        v[k] = g[k] * is[k] * (dd - s1[k] - xh * s2[k]);
+      }
+      LoadVec<T, 8>::st(dx + r * C + tx * 8, v);
+    }
+  }
+  grid.sync();
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < 2 * C; i += 256) acc[i] = 0.0;
+}
+
+// grid of a cooperative BatchNorm launch: every block must be resident at once
+template <typename K>
+int bn_coop_grid(K kern, int64_t n, int ry, size_t smem) {
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, 256, smem) != cudaSuccess || v < 1) v = 1;
+    per_sm = v > 4 ? 4 : v;
+  }
+  int64_t g = (n + (int64_t)ry * 4 - 1) / ((int64_t)ry * 4);         // >= 4 rows per thread and phase
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+// fp64 accumulators of the fused kernels: 2 x 2048 doubles per (device, stream), allocated and zeroed once; every
+// fused kernel finds them zero and leaves them zero, so no memset precedes a launch.  nullptr if allocation fails
+// (the caller then takes the four-launch path).
+double* zero_scratch(cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, double*> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = table.find({dev, s});
+  if (it != table.end()) return it->second;
+  double* p = nullptr;
+  if (cudaMalloc(&p, 2 * 2048 * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+  else if (cudaMemsetAsync(p, 0, 2 * 2048 * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
+  table[{dev, s}] = p;
+  return p;
+}
+bool bn_fused_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SCN_B200_BN_FUSED");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 template <typename T, int VEC>
 __global__ void k_bn_bwd_apply(const T* __restrict__ x, const T* __restrict__ dout, int64_t nvec, int C, int64_t n,
                                const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -401,6 +619,19 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
                  double* ws, T* out, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
+  double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
+  if (zws != nullptr) {
+    ws = zws;                                 // library-owned accumulators, all zero between kernels
+    const int ry = 256 / (C >> 3);
+    const size_t smem = (size_t)ry * (C >> 3) * 16 * sizeof(float);
+    auto kern = k_bn_fwd_fused<T>;
+    const int g = bn_coop_grid(kern, n, ry, smem);
+    void* args[] = {(void*)&x, (void*)&n, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&rm, (void*)&rv, (void*)&eps,
+                    (void*)&momentum, (void*)&leak, (void*)&save_mean, (void*)&save_invstd, (void*)&ws, (void*)&out};
+    SCN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s));
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   if (training) {
     SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
     if (n > 0) {
@@ -432,10 +663,23 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
 
 template <typename T>
 int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamma, const float* beta,
-                  const float* mean, const float* invstd, int training, float leak, double* ws, T* dx, float* dgamma,
-                  float* dbeta, int accumulate, cudaStream_t s) {
+                  const float* mean, const float* invstd, int training, float leak, double* ws, T* dx,
+                  float* dgamma, float* dbeta, int accumulate, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) & 15) == 0;
+  double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
+  if (zws != nullptr) {
+    ws = zws;
+    const int ry = 256 / (C >> 3);
+    const size_t smem = (size_t)ry * (C >> 3) * 16 * sizeof(float);
+    auto kern = k_bn_bwd_fused<T>;
+    const int g = bn_coop_grid(kern, n, ry, smem);
+    void* args[] = {(void*)&x, (void*)&dout, (void*)&n, (void*)&C, (void*)&mean, (void*)&invstd, (void*)&gamma,
+                    (void*)&beta, (void*)&leak, (void*)&ws, (void*)&dx, (void*)&dgamma, (void*)&dbeta, (void*)&accumulate};
+    SCN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s));
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
   if (n > 0) {
     int rc = vec8 ? launch_col_reduce<8>(BnBwdF<T, 8>{x, dout, mean, invstd, gamma, beta, leak, C}, n, C, ws, s)
