@@ -217,17 +217,45 @@ def run_ours(args, rank, world, local_rank):
     n_voxels = int(np.mean([h["coords"].shape[0] for h in pool]))
     h2d_bytes = int(np.mean([h["coords"].numel() * 8 + h["feats"].numel() * 4 + 4 * 8 * args.batch for h in pool]))
 
+    # Both loops tell the trainer which batch comes next (what a data loader with one batch of look-ahead knows), so the
+    # next step's rulebooks -- a function of coordinates only -- are built on the rulebook stream during this step's
+    # backward (--no-prefetch turns that off).
+    tuples = [(d["coords"], d["feats"], d["bs"]) for d in dpool]
+
     def step_resident(i):
         d = dpool[i % len(dpool)]
-        return trainer.step((d["coords"], d["feats"], d["bs"]), d["labels"])
+        nxt = None if args.no_prefetch else tuples[(i + 1) % len(dpool)]
+        return trainer.step(tuples[i % len(dpool)], d["labels"], prefetch=nxt)
+
+    copy_stream = torch.cuda.Stream(device=dev)
+    staged = {}
+
+    def upload(i):
+        """H2D of step i's inputs from pinned host memory on a copy stream -> (batch tuple, labels, done event)."""
+        h = pool[i % len(pool)]
+        with torch.cuda.stream(copy_stream):
+            c = h["coords"].to(dev, non_blocking=True)
+            f = h["feats"].to(dev, non_blocking=True)
+            lab = {k: v.to(dev, non_blocking=True) for k, v in h["labels"].items()}
+            ev = copy_stream.record_event()
+        return (c, f, h["bs"]), lab, ev
 
     def step_e2e(i):
-        h = pool[i % len(pool)]
-        c = h["coords"].to(dev, non_blocking=True)
-        f = h["feats"].to(dev, non_blocking=True)
-        lab = {k: v.to(dev, non_blocking=True) for k, v in h["labels"].items()}
-        loss = trainer.step((c, f, h["bs"]), lab)
+        # this step's inputs: uploaded during the previous step (or now, for the first one); the next step's upload is
+        # issued before this step runs so it overlaps it -- every step still copies exactly one batch host -> device
+        batch, lab, ev = staged.pop(i) if i in staged else upload(i)
+        main = torch.cuda.current_stream(dev)
+        main.wait_event(ev)
+        for t in [batch[0], batch[1]] + list(lab.values()):
+            t.record_stream(main)
+        nxt, nxt_ev = None, None
+        if not args.no_prefetch and i + 1 < e2e_steps[0]:
+            staged[i + 1] = upload(i + 1)
+            nxt, nxt_ev = staged[i + 1][0], staged[i + 1][2]
+        loss = trainer.step(batch, lab, prefetch=nxt, prefetch_ready=nxt_ev)
         return float(loss.detach().cpu())          # D2H of the step's result
+
+    e2e_steps = [args.steps]
 
     def barrier():
         if world > 1:
@@ -355,6 +383,7 @@ def main():
     ap.add_argument("--pool", type=int, default=4, help="distinct synthetic batches cycled per rank")
     ap.add_argument("--cpu-events", type=int, default=8, help="events per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="do not build the next batch's rulebooks ahead")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

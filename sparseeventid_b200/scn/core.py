@@ -83,14 +83,18 @@ class _RulebookStream:
     def __enter__(self):
         md = self.md
         self.main = torch.cuda.current_stream(md.device)
-        self.active = _side_enabled and md.device.type == "cuda"
+        self.prefetch = md._prefetch is not None
+        self.active = (_side_enabled or self.prefetch) and md.device.type == "cuda"
         if self.active:
             side = _side_streams.get(md.device)
             if side is None:
                 side = _side_streams[md.device] = torch.cuda.Stream(device=md.device)
             self.side = side
-            if self.join_first:              # the coordinates were produced on the caller's stream
-                side.wait_stream(self.main)
+            if self.join_first:
+                if not self.prefetch:        # the coordinates were produced on the caller's stream
+                    side.wait_stream(self.main)
+                elif md._prefetch["ready"] is not None:      # ... or by a copy whose completion event we were given
+                    side.wait_event(md._prefetch["ready"])
             torch.cuda.set_stream(side)
         return self
 
@@ -98,14 +102,20 @@ class _RulebookStream:
         if self.active:
             for t in tensors:
                 if t is not None:
-                    t.record_stream(self.main)
+                    if self.prefetch:        # the consuming stream is not known yet: registered when the metadata is taken
+                        self.md._prefetch["tensors"].append(t)
+                    else:
+                        t.record_stream(self.main)
         return tensors[0] if len(tensors) == 1 else tensors
 
     def __exit__(self, *exc):
         if self.active:
             ev = self.side.record_event()
             torch.cuda.set_stream(self.main)
-            self.main.wait_event(ev)
+            if self.prefetch:
+                self.md._prefetch["event"] = ev      # nobody waits yet: that is the point of prefetching
+            else:
+                self.main.wait_event(ev)
         return False
 
 
@@ -120,6 +130,35 @@ class Metadata:
         self.n_input = 0
         self.batch_size = 0
         self.input_spatial = None
+        self.plan = []                  # rulebooks in the order the network asked for them (replayed by prefetch())
+        self._prefetch = None           # while being built ahead of use: {"ready", "event", "tensors"}
+
+    # -- input ---------------------------------------------------------------------------------
+    def build_input(self, coords, spatial):
+        """InputLayer rules: packed keys, first-appearance row numbering, hash table of the input level."""
+        spatial = tuple(spatial)
+        with self.rulebook_stream(join_first=True) as rs:
+            keys = ops.pack_coords(coords, self.dimension)
+            rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
+            lvl = self.add_level(spatial, keys_out, (tk, tv, cap))
+            rs.publish(rows, keys_out, tk, tv)
+        self.row_of_input = rows
+        self.n_input = int(keys.shape[0])
+        self.input_spatial = spatial
+        return lvl
+
+    def adopt(self):
+        """A prefetched metadata becomes the current one: its tensors (allocated on the rulebook stream) are registered
+        with the consuming stream, which waits for the rulebook stream's last event."""
+        pf, self._prefetch = self._prefetch, None
+        if pf is None:
+            return self
+        main = torch.cuda.current_stream(self.device)
+        for t in pf["tensors"]:
+            t.record_stream(main)
+        if pf["event"] is not None:
+            main.wait_event(pf["event"])
+        return self
 
     # -- levels ------------------------------------------------------------------------------
     def rulebook_stream(self, join_first=False) -> _RulebookStream:
@@ -145,6 +184,7 @@ class Metadata:
         key = (tuple(spatial), tuple(filt))
         if key not in self.subm:
             lvl = self.levels[tuple(spatial)]
+            self.plan.append(("subm", tuple(spatial), tuple(filt)))
             with self.rulebook_stream() as rs:
                 self.subm[key] = rs.publish(
                     ops.subm_rulebook(lvl.keys, lvl.table_keys, lvl.table_vals, lvl.cap, pad3(filt, 1)))
@@ -166,6 +206,7 @@ class Metadata:
             out_spatial.append((spatial[a] - filt[a]) // stride[a] + 1)
         out_spatial = tuple(out_spatial)
         lvl = self.levels[spatial]
+        self.plan.append(("strided", spatial, filt, stride))
         with self.rulebook_stream() as rs:
             keys_out, out_row, off = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
             if out_spatial in self.levels:
@@ -185,6 +226,45 @@ class Metadata:
         rule = StridedRule(out_spatial, down, up, K, lvl.n, n_out)
         self.strided[key] = rule
         return rule
+
+
+# ---------------------------------------------------------------------------------------------
+# Rulebook prefetch: rulebooks depend on coordinates only, so a data pipeline that knows its next batch can have them
+# built on the rulebook stream while the current step's backward runs (the stem's 125-offset table alone is ~1.2 ms of
+# otherwise exposed time at the start of a step).  Explicit and identity-based: the prefetched metadata is used only
+# if InputLayer later receives THE SAME coordinate tensor object.
+# ---------------------------------------------------------------------------------------------
+_prefetched = {}
+
+
+def prefetch(coords, dimension, spatial_size, plan, ready_event=None):
+    """Builds InputLayer rules and the rulebooks listed in `plan` (a previous Metadata.plan) for `coords` ahead of use.
+    `ready_event`: CUDA event after which `coords` is valid (e.g. the end of its host->device copy), or None if it
+    already is."""
+    coords = torch.as_tensor(coords)
+    if not coords.is_cuda:
+        return None
+    md = Metadata(dimension, coords.device)
+    md._prefetch = {"ready": ready_event, "event": None, "tensors": []}
+    md.build_input(coords, tuple(int(v) for v in spatial_size))
+    for item in list(plan):
+        try:
+            if item[0] == "subm":
+                md.subm_table(item[1], item[2])
+            else:
+                md.strided_rule(item[1], item[2], item[3])
+        except KeyError:            # a level the plan expects does not exist for this input: leave the rest to the forward
+            break
+    _prefetched.clear()             # one batch ahead
+    _prefetched[id(coords)] = (coords, md, dimension, tuple(int(v) for v in spatial_size))
+    return md
+
+
+def take_prefetched(coords, dimension, spatial):
+    hit = _prefetched.pop(id(coords), None)
+    if hit is None or hit[0] is not coords or hit[2] != dimension or hit[3] != tuple(spatial):
+        return None
+    return hit[1].adopt()
 
 
 class Pending:

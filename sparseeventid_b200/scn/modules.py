@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from . import _ext, config, dense_view, ops
+from . import _ext, config, core, dense_view, ops
 from . import functional as F
 from .core import Metadata, Pending, SparseConvNetTensor, as_tuple
 
@@ -62,16 +62,16 @@ class InputLayer(nn.Module):
             coords = coords.to(feats.device, non_blocking=True)
         if coords.dim() != 2 or coords.shape[1] not in (self.dimension, self.dimension + 1):
             raise ValueError(f"coords must be [N, {self.dimension}] or [N, {self.dimension + 1}]")
-        md = Metadata(self.dimension, feats.device)
         sp = tuple(int(v) for v in self.spatial_size)
-        with md.rulebook_stream(join_first=True) as rs:
-            keys = ops.pack_coords(coords, self.dimension)
-            rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
-            lvl = md.add_level(sp, keys_out, (tk, tv, cap))
-            rs.publish(rows, keys_out, tk, tv)
-        md.row_of_input = rows
-        md.n_input = int(keys.shape[0])
-        md.input_spatial = sp
+        md = core.take_prefetched(coords, self.dimension, sp)        # built ahead by scn.prefetch() for this very tensor?
+        if md is None:
+            md = Metadata(self.dimension, feats.device)
+            lvl = md.build_input(coords, sp)
+        else:
+            lvl = md.levels[sp]
+        rows = md.row_of_input
+        keys_out = lvl.keys
+        self._last_plan = md.plan                                    # filled as the network asks for rulebooks
         if batch_size > 0 or lvl.n == 0:
             md.batch_size = batch_size            # given by the caller (the reference always passes it): no device sync
         else:

@@ -121,11 +121,27 @@ class Trainer:
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: warmup_flat_lr(s, peak_lr))
         self.model.train()
 
-    def step(self, batch, labels):
-        """batch: (coords [N,4], features [N,1], batch_size) on self.device; labels: dict of int64 [B]."""
+    def prefetch_rulebooks(self, next_batch, ready_event=None):
+        """Has the rulebooks of the NEXT batch built on the rulebook stream now (they depend on coordinates only), so
+        they overlap this step's backward instead of stalling the start of the next step.  A no-op until one forward
+        has recorded which rulebooks the network asks for, or on modules without the mechanism (oracle shim)."""
+        il = getattr(self, "_input_layer", None)
+        if il is None:
+            cands = [m for m in self.model.modules() if hasattr(m, "_last_plan")]
+            il = self._input_layer = cands[0] if cands else False
+        if not il or not getattr(il, "_last_plan", None):
+            return
+        from .scn import core
+        core.prefetch(next_batch[0], il.dimension, il.spatial_size, il._last_plan, ready_event)
+
+    def step(self, batch, labels, prefetch=None, prefetch_ready=None):
+        """batch: (coords [N,4], features [N,1], batch_size) on self.device; labels: dict of int64 [B].
+        prefetch: the next step's batch tuple (same tensor objects that will be passed then), optional."""
         self.arena.zero()
         logits = self.model(batch)
         loss = networks.focal_loss(labels, logits)
+        if prefetch is not None:
+            self.prefetch_rulebooks(prefetch, prefetch_ready)
         loss.backward()
         self.arena.finish()
         self.opt.step()

@@ -417,3 +417,41 @@ def test_device_input_transform_matches_host_transform(scn, dataset):
     xb = scn.InputLayer(3, grid)((cg, fg, bg))
     assert torch.equal(xa.metadata.row_of_input, xb.metadata.row_of_input)
     assert torch.equal(xa.features, xb.features)
+
+
+def test_rulebook_prefetch_gives_identical_results(scn):
+    """scn.prefetch builds InputLayer rules + the recorded rulebook plan for the NEXT batch on the rulebook stream;
+    a forward/backward that adopts them must be bit-identical to one that builds them itself, and a different
+    tensor object must never pick them up."""
+    from sparseeventid_b200.scn import core
+    scn.set_precision("bf16")
+    torch.manual_seed(1)
+    c = 32
+    net = torch.nn.Sequential(
+        scn.SubmanifoldConvolution(3, 1, c, 3, True), scn.BatchNormLeakyReLU(c),
+        scn.Convolution(3, c, 2 * c, 2, 2, False), scn.SubmanifoldConvolution(3, 2 * c, 2 * c, 3, False),
+        scn.SparseToDense(3, 2 * c)).cuda()
+    il = scn.InputLayer(3, [24, 24, 24])
+
+    def run(coords, feats):
+        net.zero_grad()
+        y = net(il((coords, feats, 3)))
+        y.float().square().sum().backward()
+        return y.detach().clone(), [p.grad.clone() for p in net.parameters()]
+
+    a = torch.as_tensor(blob_sites(300, (24, 24, 24), 3, seed=5)).cuda()
+    b = torch.as_tensor(blob_sites(280, (24, 24, 24), 3, seed=6)).cuda()
+    fa, fb = torch.randn(a.shape[0], 1).cuda(), torch.randn(b.shape[0], 1).cuda()
+    run(a, fa)                                           # records the plan
+    want_y, want_g = run(b, fb)
+    run(a, fa)
+    md = core.prefetch(b, 3, [24, 24, 24], il._last_plan)
+    assert md is not None and len(md.subm) == 2 and len(md.strided) == 1
+    assert core.take_prefetched(b.clone(), 3, (24, 24, 24)) is None       # another tensor object: not adopted
+    core.prefetch(b, 3, [24, 24, 24], il._last_plan)
+    got_y, got_g = run(b, fb)
+    assert not core._prefetched                                            # it was consumed
+    assert torch.equal(got_y, want_y)
+    for g, w in zip(got_g, want_g):
+        scale = float(w.abs().max()) + 1e-12
+        assert float((g - w).abs().max()) <= 2e-4 * scale                  # wgrad atomics: fp32 summation order only
