@@ -21,9 +21,16 @@ from . import networks
 class FlatGradArena:
     """All parameter gradients as views into one fp32 buffer; bucketed async all-reduce from hooks."""
 
-    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 32 << 20, process_group=None):
+    def __init__(self, params: List[torch.nn.Parameter], bucket_bytes: int = 32 << 20, process_group=None,
+                 overlap: bool = False):
+        """overlap=False (default): ONE all-reduce of the whole arena after the backward.  The convolution kernels
+        are persistent (one CTA per SM, 220 KB of shared memory each): a NCCL kernel that runs concurrently takes SMs
+        away and every overlapped convolution then needs a second wave -- measured at 2 GPUs, bucketed overlap cost
+        2.8 ms per step against ~0.5 ms for the exposed single all-reduce (83.5 MB over NVLink 5).
+        overlap=True: bucketed asynchronous all-reduces launched from gradient-ready hooks (DDP style)."""
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
+        self.overlap = overlap
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         total = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -56,12 +63,12 @@ class FlatGradArena:
         for p in self.params:
             if getattr(p, "_scn_param", False):
                 p._scn_direct_grad = True
-                if self.world > 1:
+                if self.world > 1 and overlap:
                     p._scn_grad_ready = self._on_grad
                     self._param_of_ptr[p.data_ptr()] = p
-            elif self.world > 1:
+            elif self.world > 1 and overlap:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
-        if self.world > 1:
+        if self.world > 1 and overlap:
             from .scn import _ext
             ext = _ext.get()
             if ext is not None:      # the C++ autograd functions report completed in-place gradients through this
@@ -82,6 +89,13 @@ class FlatGradArena:
     def finish(self):
         """Waits for the in-flight bucket all-reduces and turns the sums into means."""
         if self.world == 1:
+            return
+        if not self.overlap:
+            if dist.get_backend(self.group) == "nccl":
+                dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+                self.flat.mul_(1.0 / self.world)
             return
         for b, left in enumerate(self._pending):      # parameters that received no gradient this step
             if left > 0:

@@ -24,7 +24,7 @@ def _model():
                                torch.nn.Linear(16, 3))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, overlap=True):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -35,7 +35,7 @@ def _worker(rank, world, port, q):
             p.data.add_(1.0)
     for p in model.parameters():
         dist.broadcast(p.data, src=0)
-    arena = FlatGradArena(list(model.parameters()), bucket_bytes=256)     # tiny buckets -> several all-reduces
+    arena = FlatGradArena(list(model.parameters()), bucket_bytes=256, overlap=overlap)   # tiny buckets -> several all-reduces
     assert len(arena.buckets) > 2
     g = torch.Generator().manual_seed(100 + rank)
     for step in range(2):
@@ -49,11 +49,12 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_flat_arena_allreduce_mean_world2():
+@pytest.mark.parametrize("overlap", [True, False])
+def test_flat_arena_allreduce_mean_world2(overlap):
     world, port = 2, _free_port()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, overlap)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
