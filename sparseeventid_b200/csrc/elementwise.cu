@@ -426,6 +426,51 @@ __global__ void __launch_bounds__(256) k_bn_bwd_fused(const T* __restrict__ x, c
     for (int i = threadIdx.x; i < 2 * C; i += 256) acc[i] = 0.0;
 }
 
+// Column sums (conv bias gradient) in ONE launch: blocks add their partial sums to the zeroed fp64 accumulators, the
+// last block to finish (atomic ticket) writes / accumulates the result and zeroes accumulators and ticket again.
+// acc: [2048] doubles (zero on entry and exit), ticket: the unsigned right behind them.
+template <typename T>
+__global__ void __launch_bounds__(256) k_col_sum_fused(const T* __restrict__ x, int64_t n, int C, double* acc,
+                                                       unsigned* ticket, float* __restrict__ out, int accumulate) {
+  extern __shared__ float sred[];                        // [RY][CV][8]
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 0.f;
+  if (ty < RY) {
+    for (int64_t r = (int64_t)blockIdx.x * RY + ty; r < n; r += (int64_t)gridDim.x * RY) {
+      float v[8];
+      LoadVec<T, 8>::ld(x + r * C + tx * 8, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += v[k];
+    }
+    float* dst = sred + ((size_t)ty * CV + tx) * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dst[k] = a[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * 8; i += 256) {
+    float sum = 0.f;
+    for (int y = 0; y < RY; ++y) sum += sred[((size_t)y * CV + (i >> 3)) * 8 + (i & 7)];
+    atomicAdd(acc + i, (double)sum);
+  }
+  __threadfence();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < C; c += 256) {
+      const double v = *reinterpret_cast<volatile double*>(acc + c);
+      out[c] = (accumulate ? out[c] : 0.f) + (float)v;
+      acc[c] = 0.0;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
 // grid of a cooperative BatchNorm launch: every block must be resident at once
 template <typename K>
 int bn_coop_grid(K kern, int64_t n, int ry, size_t smem) {
@@ -440,7 +485,8 @@ int bn_coop_grid(K kern, int64_t n, int ry, size_t smem) {
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
-// fp64 accumulators of the fused kernels: 2 x 2048 doubles per (device, stream), allocated and zeroed once; every
+// fp64 accumulators of the fused kernels: 2 x 2048 doubles (BatchNorm) + 2048 doubles and a ticket (column sums) per
+// (device, stream), allocated and zeroed once; every
 // fused kernel finds them zero and leaves them zero, so no memset precedes a launch.  nullptr if allocation fails
 // (the caller then takes the four-launch path).
 double* zero_scratch(cudaStream_t s) {
@@ -452,8 +498,8 @@ double* zero_scratch(cudaStream_t s) {
   auto it = table.find({dev, s});
   if (it != table.end()) return it->second;
   double* p = nullptr;
-  if (cudaMalloc(&p, 2 * 2048 * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
-  else if (cudaMemsetAsync(p, 0, 2 * 2048 * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
+  if (cudaMalloc(&p, (3 * 2048 + 2) * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+  else if (cudaMemsetAsync(p, 0, (3 * 2048 + 2) * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
   table[{dev, s}] = p;
   return p;
 }
@@ -780,6 +826,27 @@ extern "C" int scn_col_sum_acc(const void* x, int dtype, int64_t n, int C, doubl
                                void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (C < 1 || !out || !stats_ws) return SCN_ERR_ARG;
+  if (n > 0 && (C % 8) == 0 && C <= 2048 && (((uintptr_t)x) & 15) == 0 && bn_fused_enabled()) {
+    double* z = zero_scratch(s);
+    if (z != nullptr) {
+      double* acc1 = z + 2 * 2048;
+      unsigned* ticket = reinterpret_cast<unsigned*>(z + 3 * 2048);
+      const int ry = 256 / (C >> 3);
+      int64_t g = (n + (int64_t)ry * 8 - 1) / ((int64_t)ry * 8);
+      if (g > (int64_t)kNumSMs * 4) g = (int64_t)kNumSMs * 4;
+      if (g < 1) g = 1;
+      const size_t smem = (size_t)ry * (C >> 3) * 8 * sizeof(float);
+      if (dtype == SCN_F32)
+        k_col_sum_fused<float><<<(unsigned)g, 256, smem, s>>>((const float*)x, n, C, acc1, ticket, out, accumulate);
+      else if (dtype == SCN_BF16)
+        k_col_sum_fused<__nv_bfloat16><<<(unsigned)g, 256, smem, s>>>((const __nv_bfloat16*)x, n, C, acc1, ticket, out,
+                                                                        accumulate);
+      else
+        return SCN_ERR_ARG;
+      SCN_LAUNCH_CHECK();
+      return SCN_OK;
+    }
+  }
   double* acc = stats_ws;
   SCN_CUDA(cudaMemsetAsync(acc, 0, 2 * (size_t)C * sizeof(double), s));
   int rc = SCN_OK;

@@ -33,9 +33,8 @@ def _grad_ready(param):
 
 
 class ConvWorkspace:
-    """Per-module device workspaces of the convolution kernels: the re-laid weight images for the forward and for the
-    dgrad, each tagged with the (version, storage) of the weight it was built from so unchanged weights are not
-    re-laid (inference, gradient accumulation), and the kernel family chosen for this shape."""
+    """Per-module device workspaces of the convolution kernels: the buffers of the re-laid weight images (forward and
+    dgrad; rebuilt on every call, see modules._ConvBase._conv) and the kernel family chosen for this shape."""
 
     __slots__ = ("fwd", "bwd", "fwd_key", "bwd_key", "path")
 
@@ -72,10 +71,8 @@ class ConvFn(Function):
             ws = owner.workspace(K, cin, cout, prec, fdt, x.device)
             if ws.path > 0 and x.dtype != fdt:
                 x = ops.convert(x, fdt)
-            key = (weight._version, weight.data_ptr())
-            out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd,
-                                          ws.fwd_key == key)
-            ws.fwd_key = key
+            # always re-laid: fused optimizers update parameters without bumping Tensor._version (see modules._conv)
+            out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False)
             ctx.ws = ws
         else:
             w3 = _w3(weight)
@@ -110,9 +107,7 @@ class ConvFn(Function):
             wimg_t, skip = None, False
             if need_dx:
                 wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
-                key = (weight._version, weight.data_ptr())
-                skip = ws.bwd_key == key
-                ws.bwd_key = key
+                skip = False
             dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
                                           ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
                                           gw if gw is not None else dw, gw is None,

@@ -133,9 +133,9 @@ class _ConvBase(nn.Module):
             ws = self.workspace(K, cin, cout, prec, fdt, x.device)
             if ws.path > 0 and x.dtype != fdt:
                 x = ops.convert(x, fdt)
-            key = (w._version, w.data_ptr())
-            skip = ws.fwd_key == key
-            ws.fwd_key = key
+            # The weight image is rebuilt on every call: there is no reliable "weights changed" signal (fused
+            # optimizers update parameters without bumping Tensor._version), and the re-layout is a ~4 us kernel.
+            skip = False
             wimg_t = None
             if x.requires_grad and torch.is_grad_enabled():
                 wimg_t = ws.bwd_buffer(K, cin, cout, prec, x.dtype, x.device)

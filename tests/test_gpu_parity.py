@@ -455,3 +455,31 @@ def test_rulebook_prefetch_gives_identical_results(scn):
     for g, w in zip(got_g, want_g):
         scale = float(w.abs().max()) + 1e-12
         assert float((g - w).abs().max()) <= 2e-4 * scale                  # wgrad atomics: fp32 summation order only
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_forward_follows_optimizer_updates(scn, fused):
+    """Regression: the re-laid weight images must track the parameters through optimizer steps.  Fused Adam updates
+    parameters WITHOUT bumping Tensor._version, so a version-keyed image cache silently froze the forward weights."""
+    scn.set_precision("bf16")
+    torch.manual_seed(2)
+    c = 32
+    net = torch.nn.Sequential(scn.SubmanifoldConvolution(3, 1, c, 3, True), scn.BatchNormLeakyReLU(c),
+                              scn.SubmanifoldConvolution(3, c, c, 3, True), scn.SparseToDense(3, c)).cuda()
+    opt = torch.optim.Adam(net.parameters(), lr=5e-2, fused=fused)
+    coords = torch.as_tensor(blob_sites(200, (16, 16, 16), 2, seed=9)).cuda()
+    feats = torch.randn(coords.shape[0], 1).cuda()
+    il = scn.InputLayer(3, [16, 16, 16])
+    y0 = net(il((coords, feats, 2))).detach().clone()
+    for _ in range(3):
+        opt.zero_grad()
+        net(il((coords, feats, 2))).float().square().mean().backward()
+        opt.step()
+    net.eval()
+    y_trained = net(il((coords, feats, 2))).detach()
+    fresh = torch.nn.Sequential(scn.SubmanifoldConvolution(3, 1, c, 3, True), scn.BatchNormLeakyReLU(c),
+                                scn.SubmanifoldConvolution(3, c, c, 3, True), scn.SparseToDense(3, c)).cuda().eval()
+    fresh.load_state_dict(net.state_dict())
+    y_fresh = fresh(il((coords, feats, 2))).detach()
+    assert torch.equal(y_trained, y_fresh)               # same parameters -> same output, whatever the history
+    assert float((y_trained - y0).abs().max()) > 1e-3    # and the three steps did change the network
