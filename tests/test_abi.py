@@ -90,3 +90,16 @@ def test_state_dict_keys_match_reference_layout():
     enc2, _ = networks.build_networks(scn, "dune2d")
     assert sum(p.numel() for p in enc2.parameters()) == 7038912
     assert enc.output_shape == [128, 32, 16, 40] and enc2.output_shape == [128, 3, 48, 32]
+
+
+def test_torch_extension_builds_and_exports_the_module_functions():
+    """The thin PyTorch C++ layer (csrc_torch/scn_torch.cpp) builds in-tree on a CPU-only box and exposes the autograd
+    functions the modules call (no compute here: they need a GPU)."""
+    from sparseeventid_b200 import build
+    from sparseeventid_b200.scn import _ext
+    path = build.build_torch_ext()
+    assert os.path.exists(path) and os.path.dirname(path).endswith("build_torch")
+    ext = _ext.get()
+    assert ext is not None
+    for name in ("conv", "batch_norm", "add_leaky", "leaky", "set_grad_ready_callback"):
+        assert hasattr(ext, name), name
