@@ -665,6 +665,7 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
                  double* ws, T* out, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
+  double* const ws_caller = ws;
   double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
   if (zws != nullptr) {
     ws = zws;                                 // library-owned accumulators, all zero between kernels
@@ -674,9 +675,12 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
     const int g = bn_coop_grid(kern, n, ry, smem);
     void* args[] = {(void*)&x, (void*)&n, (void*)&C, (void*)&gamma, (void*)&beta, (void*)&rm, (void*)&rv, (void*)&eps,
                     (void*)&momentum, (void*)&leak, (void*)&save_mean, (void*)&save_invstd, (void*)&ws, (void*)&out};
-    SCN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s));
-    SCN_LAUNCH_CHECK();
-    return SCN_OK;
+    if (cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s) == cudaSuccess) {
+      SCN_LAUNCH_CHECK();
+      return SCN_OK;
+    }
+    (void)cudaGetLastError();                   // cooperative launch refused (e.g. MPS limits): four-launch path below
+    ws = ws_caller;
   }
   if (training) {
     SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
@@ -713,6 +717,7 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
                   float* dgamma, float* dbeta, int accumulate, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) & 15) == 0;
+  double* const ws_caller = ws;
   double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
   if (zws != nullptr) {
     ws = zws;
@@ -722,9 +727,12 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
     const int g = bn_coop_grid(kern, n, ry, smem);
     void* args[] = {(void*)&x, (void*)&dout, (void*)&n, (void*)&C, (void*)&mean, (void*)&invstd, (void*)&gamma,
                     (void*)&beta, (void*)&leak, (void*)&ws, (void*)&dx, (void*)&dgamma, (void*)&dbeta, (void*)&accumulate};
-    SCN_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s));
-    SCN_LAUNCH_CHECK();
-    return SCN_OK;
+    if (cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s) == cudaSuccess) {
+      SCN_LAUNCH_CHECK();
+      return SCN_OK;
+    }
+    (void)cudaGetLastError();
+    ws = ws_caller;
   }
   SCN_CUDA(cudaMemsetAsync(ws, 0, 2 * (size_t)C * sizeof(double), s));
   if (n > 0) {

@@ -29,10 +29,16 @@ def get():
         return None
     import torch  # noqa: F401  (libtorch must be mapped before the extension)
     _lib.load()
-    ctypes.CDLL(_lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)       # resolves the extension's NEEDED libscn_b200.so
-    loader = importlib.machinery.ExtensionFileLoader(TORCH_EXT_NAME, TORCH_EXT_SO)
-    spec = importlib.util.spec_from_loader(TORCH_EXT_NAME, loader)
-    mod = importlib.util.module_from_spec(spec)
-    loader.exec_module(mod)
-    _mod = mod
+    try:
+        ctypes.CDLL(_lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)   # resolves the extension's NEEDED libscn_b200.so
+        loader = importlib.machinery.ExtensionFileLoader(TORCH_EXT_NAME, TORCH_EXT_SO)
+        spec = importlib.util.spec_from_loader(TORCH_EXT_NAME, loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        _mod = mod
+    except (ImportError, OSError) as e:       # e.g. built against another torch: the Python functions take over
+        import warnings
+        warnings.warn(f"scn_b200_torch.so could not be loaded ({e}); using the Python autograd functions "
+                      "(same CUDA kernels through the same C ABI)")
+        _mod = None
     return _mod
