@@ -11,8 +11,10 @@ Workload at N=1 = BASELINE.json configs[2] per GPU ("3D sparse ResNet training, 
 parallel, batch 64/GPU, bf16 tensor-core convs"); weak scaling (64 events on every rank).
 
 Prints ONE JSON line (rank 0).  `value` = events/s with the batch already resident in HBM;
-`e2e` = events/s through the public module API starting from pinned HOST buffers (H2D of the SCN input
-tuple + labels, D2H of the loss, every step).  `roofline` describes the dominant kernel family (the
+`e2e` = events/s through the public module API starting from pinned HOST buffers: every step copies one batch
+(SCN input tuple + labels) host -> device on a copy stream, one step ahead like a data loader, and copies its loss
+device -> host into pinned memory (consumed one step later).  Both loops tell the trainer which batch comes next so
+that its rulebooks are built during the current backward (--no-prefetch disables that).  `roofline` describes the dominant kernel family (the
 gather-GEMM convolution kernels), timed live with CUDA events on the launching stream in a separate
 instrumented pass after the timed region.  `cpu_baseline` = the oracle port of SparseConvNet's CPU
 algorithm on the host cores, on a bounded sample.  `--impl reference` times that CPU arm alone.

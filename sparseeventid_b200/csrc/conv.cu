@@ -12,8 +12,8 @@ bool scn_tc_shape_ok(int K, int n_in, int n_out);
 size_t scn_tc_image_bytes(int K, int n_in, int n_out);
 int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s);
 bool scn_wgrad_tc_enabled();
-int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16* dout, const int32_t* nbr, int K,
-                 int64_t n_rows, int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s);
+int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_t* nbr, int K, int64_t n_rows,
+                 int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s);
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
                    cudaStream_t s);
@@ -601,11 +601,9 @@ extern "C" int scn_conv_wgrad(const void* in, int in_dtype, const void* dout, in
   if (precision == SCN_PREC_FP32 && (in_dtype != SCN_F32 || dout_dtype != SCN_F32)) return SCN_ERR_ARG;
   if (precision == SCN_PREC_BF16 && in_dtype == SCN_BF16 && dout_dtype == SCN_BF16 && !scn_tc_disabled() &&
       scn_wgrad_tc_enabled() && (n_pad & 127) == 0) {
-    // tcgen05 path; n_in_rows is not part of this entry point's signature: every gathered row index comes from the
-    // table, and the 32-bit offset check inside only needs an upper bound, for which n_pad of the FORWARD rows is not
-    // available here -> use the largest row count a 32-bit offset allows
-    int rc = scn_wgrad_tc((const __nv_bfloat16*)in, (int64_t)(0xfffffffeull / (uint64_t)((n_in >> 3) > 0 ? (n_in >> 3) : 1)) - 1,
-                          (const __nv_bfloat16*)dout, nbr, K, n_rows, n_pad, n_in, n_out, dW, s);
+    // tcgen05 path.  The number of rows of `in` is not part of this entry point's signature; the kernel addresses
+    // gathered rows through 32-bit offsets in 16-byte units, i.e. feature matrices up to 64 GB.
+    int rc = scn_wgrad_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, nbr, K, n_rows, n_pad, n_in, n_out, dW, s);
     if (rc != SCN_ERR_UNSUPPORTED) return rc;
   }
   if (mma_ok(K, n_in, n_out, precision) && in_dtype == dout_dtype) {

@@ -318,11 +318,11 @@ bool scn_wgrad_tc_enabled() {
 }
 
 // dW[K][Cin][Cout] += ...; x, dout bf16.  Returns SCN_ERR_UNSUPPORTED for shapes outside the kernel (caller falls back).
-int scn_wgrad_tc(const __nv_bfloat16* x, int64_t n_in_rows, const __nv_bfloat16* dout, const int32_t* nbr, int K,
-                 int64_t n_rows, int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s) {
+// Gathered rows are addressed through 32-bit offsets in 16-byte units: x and dout up to 64 GB each.
+int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_t* nbr, int K, int64_t n_rows,
+                 int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s) {
   if ((Cin % 32) || (Cout % 32) || Cin < 32 || Cout < 32 || Cin > 256 || Cout > 256 || K < 1) return SCN_ERR_UNSUPPORTED;
-  if ((uint64_t)n_in_rows * (uint64_t)(Cin >> 3) >= 0xffffffffull || (uint64_t)n_rows * (uint64_t)(Cout >> 3) >= 0xffffffffull)
-    return SCN_ERR_UNSUPPORTED;
+  if ((uint64_t)n_rows * (uint64_t)(Cout >> 3) >= 0xffffffffull) return SCN_ERR_UNSUPPORTED;
   if (n_pad < ((n_rows + 127) / 128) * 128) return SCN_ERR_ARG;      // whole 128-row blocks are read
   wg::Params p;
   p.x = x; p.dout = dout; p.nbr = nbr; p.dW = dW; p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.Cin = Cin; p.Cout = Cout;
