@@ -230,6 +230,16 @@ int scn_rows_gather(const void* src, int dtype, const int32_t* rows, int64_t n_r
 int scn_rows_scatter_add(const void* src, int dtype, const int32_t* rows, int64_t n_rows, int C,
                          float* out_f32, void* stream);
 
+/* scn.AveragePooling rows (pool_size == pool_stride; reference call site
+ * src/networks/sparse_building_blocks.py:150-154): out[r, :] = scale * sum over the k < K table
+ * entries nbr[k * n_pad + r] >= 0 of x[that row, 0..C), fp32 accumulation in ascending k.  Forward:
+ * nbr = the strided rule's [K][n_out_pad] table, scale = 1 / pool volume (SparseConvNet divides by
+ * the pool volume, not by the number of active inputs).  Backward: the same call with the
+ * transposed [K][n_in_pad] table on d(out).  ldx = row stride of x in elements (>= C), so that
+ * nFeaturesToDrop can read a column window of a wider matrix; out is dense [n_rows, C]. */
+int scn_pool_rows(const void* x, int dtype, int ldx, const int32_t* nbr, int K, int64_t n_rows,
+                  int64_t n_pad, int C, float scale, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * larcv batch-filler array -> SCN input tuple on the device (replaces the host numpy transforms
  * larcvsparse_to_scnsparse_3d / _2d, src/io/data_transforms.py:21-49,198-252).

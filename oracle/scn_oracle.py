@@ -323,6 +323,38 @@ def swap_rules(rules):
 
 
 # ----------------------------------------------------------------------------
+# AveragePooling (sparse_building_blocks.py:150-154, the non-default ``Pooling`` down-sampling branch)
+# ----------------------------------------------------------------------------
+
+
+def average_pooling_forward(x: torch.Tensor, rules, n_out: int, volume: int, n_drop: int = 0):
+    """out[o] = (1/volume) * sum over (i,o) in the strided rulebook of x[i, n_drop:]  [SCN-recalled].
+
+    SCN's AveragePooling walks the same rulebook as a Convolution with filter == pool_size, stride == pool_stride and
+    divides by the pool volume -- inactive sites count as zeros, which is what makes it equal to a dense
+    ``avg_pool3d`` on the zero-filled volume at every active output site.  The first ``n_drop`` feature planes are
+    skipped (SCN ``nFeaturesToDrop``)."""
+    out = torch.zeros((n_out, x.shape[1] - n_drop), dtype=x.dtype)
+    for r in rules:
+        if len(r) == 0:
+            continue
+        r = torch.as_tensor(np.asarray(r), dtype=torch.long)
+        out.index_add_(0, r[:, 1], x.index_select(0, r[:, 0])[:, n_drop:])
+    return out / volume
+
+
+def average_pooling_backward(dout: torch.Tensor, rules, n_in: int, volume: int, n_drop: int = 0):
+    """dx[i, n_drop:] = dout[o] / volume for the (single) pair (i,o) of every input row; dropped planes get zeros."""
+    dx = torch.zeros((n_in, dout.shape[1] + n_drop), dtype=dout.dtype)
+    for r in rules:
+        if len(r) == 0:
+            continue
+        r = torch.as_tensor(np.asarray(r), dtype=torch.long)
+        dx[:, n_drop:].index_add_(0, r[:, 0], dout.index_select(0, r[:, 1]) / volume)
+    return dx
+
+
+# ----------------------------------------------------------------------------
 # BatchNormalization (+ fused leaky ReLU)  (sparse_building_blocks.py:39,122)
 # ----------------------------------------------------------------------------
 

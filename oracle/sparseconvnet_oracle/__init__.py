@@ -20,7 +20,7 @@ from .. import scn_oracle as O
 
 __all__ = [
     "SparseConvNetTensor", "Metadata", "InputLayer", "OutputLayer", "SubmanifoldConvolution",
-    "Convolution", "Deconvolution", "BatchNormalization", "BatchNormReLU", "BatchNormLeakyReLU",
+    "Convolution", "Deconvolution", "AveragePooling", "BatchNormalization", "BatchNormReLU", "BatchNormLeakyReLU",
     "LeakyReLU", "ReLU", "Tanh", "Sigmoid", "Identity", "AddTable", "SparseToDense", "Sequential",
 ]
 
@@ -199,6 +199,18 @@ class _ConvFn(torch.autograd.Function):
         return _rs(dx), dw.view_as(weight), db, None, None
 
 
+class _AvgPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rules, n_out, volume, n_drop):
+        ctx.rules, ctx.n_in, ctx.volume, ctx.n_drop = rules, x.shape[0], volume, n_drop
+        return _rs(O.average_pooling_forward(x, rules, n_out, volume, n_drop))
+
+    @staticmethod
+    def backward(ctx, dout):
+        return _rs(O.average_pooling_backward(dout.contiguous(), ctx.rules, ctx.n_in, ctx.volume, ctx.n_drop)), \
+            None, None, None, None
+
+
 class _BNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, gamma, beta, rm, rv, training, eps, momentum, leak):
@@ -372,6 +384,26 @@ class Deconvolution(nn.Module):
         out = SparseConvNetTensor(metadata=md, spatial_size=torch.LongTensor(list(fine)))
         out.features = _ConvFn.apply(input.features, self.weight, self.bias, O.swap_rules(rules),
                                      md.levels[fine].shape[0])
+        return out
+
+
+class AveragePooling(nn.Module):
+    """(dimension, pool_size, pool_stride, nFeaturesToDrop=0)  (sparse_building_blocks.py:150-154)."""
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        super().__init__()
+        self.dimension = dimension
+        self.pool_size = O.as_triple(pool_size, dimension)
+        self.pool_stride = O.as_triple(pool_stride, dimension)
+        self.pool_volume = int(np.prod(self.pool_size))
+        self.nFeaturesToDrop = int(nFeaturesToDrop)
+
+    def forward(self, input):
+        md, sp = input.metadata, _sp(input)
+        out_sp, rules = md.get_strided(sp, self.pool_size, self.pool_stride)
+        out = SparseConvNetTensor(metadata=md, spatial_size=torch.LongTensor(list(out_sp)))
+        out.features = _AvgPoolFn.apply(input.features, rules, md.levels[out_sp].shape[0], self.pool_volume,
+                                        self.nFeaturesToDrop)
         return out
 
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "scn_input_layer_forward": (_i, [_p, _p, _i64, _i64, _i, _i, _p, _i, _p, _p]),
     "scn_rows_gather": (_i, [_p, _i, _p, _i64, _i, _p, _i, _p]),
     "scn_rows_scatter_add": (_i, [_p, _i, _p, _i64, _i, _p, _p]),
+    "scn_pool_rows": (_i, [_p, _i, _i, _p, _i, _i64, _i64, _i, _f, _p, _p]),
     "scn_larcv_count": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
     "scn_larcv_compact": (_i, [_p, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p]),
     "scn_sparse_to_dense_forward": (_i, [_p, _i, _p, _i64, _i, _i, _i, _i, _i, _p, _p]),

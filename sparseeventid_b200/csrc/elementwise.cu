@@ -621,6 +621,36 @@ __global__ void k_rows_scatter_add(const TI* __restrict__ src, const int32_t* __
   atomicAdd(out + (int64_t)rows[r] * C + c, Elem<TI>::ld(src + i));
 }
 
+// AveragePooling rows: out[r, :] = scale * sum_k x[nbr[k][r], :] over the table entries that exist (k ascending, fp32
+// accumulation: deterministic).  The same kernel is the backward with the transposed table.  ldx = source row stride
+// in elements (nFeaturesToDrop reads a column window of a wider matrix).
+template <typename T, int V>
+__global__ void k_pool_rows(const T* __restrict__ x, int ldx, const int32_t* __restrict__ nbr, int K, int64_t n_rows,
+                            int64_t n_pad, int C, float scale, T* __restrict__ out) {
+  const int cg = C / V;
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_rows * cg) return;
+  int64_t r = i / cg;
+  int c = (int)(i - r * cg) * V;
+  float acc[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) acc[v] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    int32_t s = __ldg(nbr + (int64_t)k * n_pad + r);
+    if (s < 0) continue;
+    const T* src = x + (int64_t)s * ldx + c;
+    if constexpr (V == 4) {
+      float4 t = ld4(src);
+      acc[0] += t.x; acc[1] += t.y; acc[2] += t.z; acc[3] += t.w;
+    } else {
+      acc[0] += Elem<T>::ld(src);
+    }
+  }
+  T* dst = out + r * C + c;
+  if constexpr (V == 4) st4(dst, make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale));
+  else Elem<T>::st(dst, acc[0] * scale);
+}
+
 template <typename T>
 __global__ void k_s2d_fwd(const T* __restrict__ x, const uint64_t* __restrict__ keys, int64_t n, int C, int s0, int s1,
                           int s2, float* __restrict__ dense) {
@@ -956,6 +986,31 @@ extern "C" int scn_rows_scatter_add(const void* src, int dtype, const int32_t* r
   else return SCN_ERR_ARG;
   SCN_LAUNCH_CHECK();
   return SCN_OK;
+}
+
+template <typename T>
+static int launch_pool_rows(const void* x, int ldx, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, int C,
+                            float scale, void* out, cudaStream_t s) {
+  const size_t vb = 4 * sizeof(T);      // bytes of one 4-element access
+  const bool vec = C % 4 == 0 && ldx % 4 == 0 && (uintptr_t)x % vb == 0 && (uintptr_t)out % vb == 0;
+  if (vec)
+    k_pool_rows<T, 4><<<grid_for(n_rows * (C / 4), 256), 256, 0, s>>>((const T*)x, ldx, nbr, K, n_rows, n_pad, C, scale,
+                                                                       (T*)out);
+  else
+    k_pool_rows<T, 1><<<grid_for(n_rows * C, 256), 256, 0, s>>>((const T*)x, ldx, nbr, K, n_rows, n_pad, C, scale,
+                                                                 (T*)out);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
+
+extern "C" int scn_pool_rows(const void* x, int dtype, int ldx, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad,
+                             int C, float scale, void* out, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n_rows == 0 || C == 0) return SCN_OK;
+  if (!x || !nbr || !out || K < 1 || C < 0 || ldx < C || n_pad < n_rows) return SCN_ERR_ARG;
+  if (dtype == SCN_F32) return launch_pool_rows<float>(x, ldx, nbr, K, n_rows, n_pad, C, scale, out, s);
+  if (dtype == SCN_BF16) return launch_pool_rows<__nv_bfloat16>(x, ldx, nbr, K, n_rows, n_pad, C, scale, out, s);
+  return SCN_ERR_ARG;
 }
 
 extern "C" int scn_sparse_to_dense_forward(const void* x, int dtype, const uint64_t* keys, int64_t n, int C, int batch,

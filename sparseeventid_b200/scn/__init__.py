@@ -2,12 +2,12 @@
 from .config import feature_dtype, get_precision, set_fusion, set_precision
 from .core import Metadata, SparseConvNetTensor, prefetch, set_rulebook_stream
 from .dense_view import SparseDenseTensor, set_lazy_dense
-from .modules import (AddTable, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, Convolution, Deconvolution,
+from .modules import (AddTable, AveragePooling, BatchNormalization, BatchNormLeakyReLU, BatchNormReLU, Convolution, Deconvolution,
                       Identity, InputLayer, LeakyReLU, OutputLayer, ReLU, Sequential, Sigmoid, SparseToDense,
                       SubmanifoldConvolution, Tanh)
 
 __all__ = [
-    "AddTable", "BatchNormalization", "BatchNormLeakyReLU", "BatchNormReLU", "Convolution", "Deconvolution",
+    "AddTable", "AveragePooling", "BatchNormalization", "BatchNormLeakyReLU", "BatchNormReLU", "Convolution", "Deconvolution",
     "Identity", "InputLayer", "LeakyReLU", "OutputLayer", "ReLU", "Sequential", "Sigmoid", "SparseToDense",
     "SubmanifoldConvolution", "Tanh", "SparseConvNetTensor", "Metadata", "set_precision", "get_precision",
     "feature_dtype", "set_lazy_dense", "SparseDenseTensor", "set_fusion", "set_rulebook_stream", "prefetch",

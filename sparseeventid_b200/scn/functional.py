@@ -232,6 +232,24 @@ class OutputLayerFn(Function):
         return ops.convert(acc, ctx.dtype), None
 
 
+class AveragePoolingFn(Function):
+    """features of scn.AveragePooling: out[q] = (1 / pool volume) * sum of the input rows of output site q."""
+
+    @staticmethod
+    def forward(ctx, x, down, up, n_out, volume, drop):
+        if x.stride(-1) != 1:
+            x = x.contiguous()
+        ctx.up, ctx.n_in, ctx.c_in, ctx.drop, ctx.scale = up, x.shape[0], x.shape[1], drop, 1.0 / volume
+        return ops.pool_rows(x, down, n_out, ctx.scale, col0=drop)
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = ops.pool_rows(dout.contiguous(), ctx.up, ctx.n_in, ctx.scale)
+        if ctx.drop:                       # dropped leading features get no gradient
+            d = torch.cat([d.new_zeros((ctx.n_in, ctx.drop)), d], 1)
+        return d, None, None, None, None, None
+
+
 class SparseToDenseFn(Function):
     @staticmethod
     def forward(ctx, x, keys, batch, spatial):

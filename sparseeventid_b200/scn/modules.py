@@ -224,6 +224,33 @@ class Deconvolution(_ConvBase):
         return _new_like(input, feats, torch.LongTensor(list(fine)))
 
 
+class AveragePooling(nn.Module):
+    """scn.AveragePooling(dimension, pool_size, pool_stride, nFeaturesToDrop=0) -- the ``Pooling`` down-sampling branch,
+    reference src/networks/sparse_building_blocks.py:150-154 (non-default ``encoder.downsampling``).  Output sites and
+    rows are those of a Convolution with the same size/stride; features are the SUM of the window's active inputs
+    divided by the pool volume (SparseConvNet's convention: inactive sites count as zeros), the first nFeaturesToDrop
+    channels left out.  No parameters."""
+
+    def __init__(self, dimension, pool_size, pool_stride, nFeaturesToDrop=0):
+        super().__init__()
+        self.dimension = dimension
+        self.pool_size = as_tuple(pool_size, dimension)
+        self.pool_stride = as_tuple(pool_stride, dimension)
+        self.pool_volume = _volume(self.pool_size)
+        self.nFeaturesToDrop = int(nFeaturesToDrop)
+
+    def forward(self, input):
+        md = input.metadata
+        feats = input.features
+        assert feats.shape[1] > self.nFeaturesToDrop, "nFeaturesToDrop leaves no feature planes"
+        rule = md.strided_rule(input._sp(), self.pool_size, self.pool_stride)
+        out = F.AveragePoolingFn.apply(feats, rule.down, rule.up, rule.n_out, self.pool_volume, self.nFeaturesToDrop)
+        return _new_like(input, out, torch.LongTensor(list(rule.out_spatial)))
+
+    def __repr__(self):
+        return f"AveragePooling {list(self.pool_size)}/{list(self.pool_stride)}"
+
+
 class BatchNormalization(nn.Module):
     """scn.BatchNormalization(nPlanes, eps=1e-4, momentum=0.9, affine=True, leakiness=1)
     -- reference src/networks/sparse_building_blocks.py:39,122.  SCN conventions (App. A.5)."""

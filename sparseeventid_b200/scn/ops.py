@@ -405,6 +405,19 @@ def rows_scatter_add(src, rows, n_out):
     return out
 
 
+def pool_rows(x, nbr, n_rows, scale, col0=0, ncol=None):
+    """out[r] = scale * sum_k x[nbr[k][r], col0:col0+ncol] over existing table entries (AveragePooling fwd / bwd)."""
+    L.require_cuda(x, "AveragePooling")
+    assert x.dim() == 2 and x.stride(1) == 1 and nbr.dtype == torch.int32
+    K, n_pad = nbr.shape
+    c = x.shape[1] - col0 if ncol is None else ncol
+    out = torch.empty((n_rows, c), dtype=x.dtype, device=x.device)
+    src = x[:, col0:] if col0 else x
+    L.check(L.lib().scn_pool_rows(src.data_ptr(), L.dtype_code(x), x.stride(0), L.ptr(nbr), K, n_rows, n_pad, c,
+                                  float(scale), L.ptr(out), L.stream()), "scn_pool_rows")
+    return out
+
+
 def sparse_to_dense_forward(x, keys, batch, spatial):
     n, c = x.shape
     dense = torch.empty((batch, c) + tuple(spatial), dtype=torch.float32, device=x.device)

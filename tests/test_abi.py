@@ -57,6 +57,8 @@ def test_module_surface_matches_reference_usage():
     assert scn.InputLayer(3, (1536, 1536, 1536)).spatial_size.tolist() == [1536] * 3
     seq = torch.nn.Sequential(scn.SparseToDense(dimension=3, nPlanes=128))
     assert isinstance(seq[0], torch.nn.Module)
+    ap = scn.AveragePooling(dimension=3, pool_size=[2, 2, 2], pool_stride=[2, 2, 2])      # sparse_building_blocks.py:150-154
+    assert ap.pool_volume == 8 and not list(ap.parameters()) and scn.AveragePooling(3, 2, 2, 1).nFeaturesToDrop == 1
     act = scn.Identity
     assert isinstance(act(), torch.nn.Module) and isinstance(scn.AddTable(), torch.nn.Module)
     # 3-D (2018-19 SCN) conv weights load into the 4-D parameter

@@ -200,3 +200,39 @@ def test_empty_and_single_site_rulebooks():
     edge = np.array([[0, 0, 65535, 0], [0, 1, 0, 0], [65535, 65535, 65535, 0], [0, 0, 0, 1]])
     r = O.submanifold_rulebook(edge, (3, 3, 3))
     assert sum(len(x) for x in r) == 4
+
+
+@pytest.mark.parametrize("pool", [(2, 2, 2), (1, 2, 2)])
+@pytest.mark.parametrize("n_drop", [0, 2])
+def test_average_pooling_dense_identity(pool, n_drop):
+    """AveragePooling == avg_pool3d of the zero-filled volume (divide by the pool volume), forward and backward."""
+    grid, B, c = (8, 6, 10), 2, 5
+    coords = random_sites(110, grid, B, seed=11)
+    n = coords.shape[0]
+    x = torch.randn(n, c, dtype=torch.float64)
+    vol = int(np.prod(pool))
+    out_coords, rules, out_sp = O.strided_rulebook(coords, pool, pool, grid)
+    out = O.average_pooling_forward(x, rules, out_coords.shape[0], vol, n_drop)
+    X = densify(x, coords, grid, B).requires_grad_(True)
+    Y = F.avg_pool3d(X[:, n_drop:], kernel_size=pool, stride=pool)
+    assert torch.allclose(O.sparse_to_dense_forward(out, out_coords, out_sp, B), Y, atol=1e-12)
+    dout = torch.randn_like(out)
+    dx = O.average_pooling_backward(dout, rules, n, vol, n_drop)
+    Y.backward(O.sparse_to_dense_forward(dout, out_coords, out_sp, B))
+    assert torch.allclose(dx, O.sparse_to_dense_backward(X.grad, coords), atol=1e-12)
+    assert n_drop == 0 or float(dx[:, :n_drop].abs().max()) == 0.0
+
+
+def test_average_pooling_module_autograd():
+    """oracle scn.AveragePooling module: output grid = Convolution's, gradient == explicit formula."""
+    import oracle.sparseconvnet_oracle as scn
+    grid, B, c = (8, 8, 8), 2, 4
+    coords = random_sites(70, grid, B, seed=13)
+    feats = torch.randn(coords.shape[0], c, dtype=torch.float64, requires_grad=True)
+    t = scn.InputLayer(3, torch.LongTensor(list(grid)), mode=3)((torch.as_tensor(coords), feats, B))
+    p = scn.AveragePooling(3, 2, 2)(t)
+    assert tuple(int(v) for v in p.spatial_size) == (4, 4, 4)
+    q = scn.Convolution(3, c, 3, 2, 2, False).double()(t)
+    assert q.features.shape[0] == p.features.shape[0]
+    p.features.sum().backward()
+    assert torch.allclose(feats.grad, torch.full_like(feats, 1 / 8))
