@@ -26,6 +26,7 @@
  *   AddTable                                            <- scn.AddTable     sparse_building_blocks.py:82,96
  *   SparseToDense_updateOutput / _updateGradInput       <- scn.SparseToDense src/networks/resnet.py:123-125
  *   OutputLayer_updateOutput / _updateGradInput         <- scn.OutputLayer  (named by the north star; no call site)
+ *   AveragePooling_updateOutput / _updateGradInput      <- scn.AveragePooling sparse_building_blocks.py:150-154
  */
 #ifndef SCN_B200_H
 #define SCN_B200_H

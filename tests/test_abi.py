@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol():
     assert lib.scn_hash_capacity(1000) == 2048 and lib.scn_hash_capacity(0) == 1024
 
 
+def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
+    """include/scn_b200.h is valid pedantic C99 (no C++/torch types at the boundary) and tools/abi_harness.c -- a
+    caller that is plain C + the CUDA runtime -- compiles and links against the library without torch."""
+    import subprocess
+    from sparseeventid_b200 import build
+    build.build()
+    probe = tmp_path / "h.c"
+    probe.write_text('#include "scn_b200.h"\nint main(void) { return scn_version() == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I", inc, str(probe)],
+                   check=True)
+    exe = tmp_path / "abi_harness"
+    subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", inc, "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tools", "abi_harness.c"), "-L", os.path.dirname(build.LIB), "-lscn_b200",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-o", str(exe)], check=True)
+    out = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "libscn_b200.so" in out and "libtorch" not in out and "libpython" not in out and "libc10" not in out
+
+
 def test_library_is_sm100a_only_and_native():
     import subprocess
     from sparseeventid_b200 import build

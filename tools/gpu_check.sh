@@ -13,3 +13,6 @@ for e in $EXPS; do
   for a in "500000 27 32 32" "317485 27 64 64" "150000 27 96 96" "60000 27 128 128" "20000 27 160 160" "7000 27 192 192" "317485 8 32 64" "317485 8 64 32"; do SCN_B200_TC_EXP=$e timeout 30 python tools/tc_profile.py $a 3; done
 done > gpurun_out/$LOG.log 2>&1
 cat gpurun_out/$LOG.log
+# the plain-C caller of the C ABI (no Python in the process)
+gcc -std=c99 -O2 -Iinclude -I/usr/local/cuda/include tools/abi_harness.c -Lsparseeventid_b200/lib -lscn_b200 \
+    -L/usr/local/cuda/lib64 -lcudart -lm -o /tmp/abi_harness && LD_LIBRARY_PATH=sparseeventid_b200/lib timeout 60 /tmp/abi_harness
