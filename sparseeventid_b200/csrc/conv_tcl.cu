@@ -1,44 +1,39 @@
-// Output-stationary gather-GEMM convolution on 5th-generation tensor cores (sm_100a only):
+// k_conv_tcl: the tcgen05 gather-GEMM convolution of conv_tc.cu driven by precomputed STAGE LISTS (stage_lists.cuh).
 //     out[o, :] = bias + sum_k  in[nbr[k][o], :] . B_k            (bf16 operands, fp32 accumulate)
 //
-// One persistent CTA per SM owns a contiguous range of 128-row output tiles (an even split of the tiles over the
-// grid) and walks it in GROUPS of T tiles whose accumulators live in TMEM together (T * n_out <= 256 columns with two
-// groups double-buffered, or <= 512 columns single-buffered when a CTA has one group anyway).  The contraction
-// (K offsets x n_in channels) is cut into stages of 64 channels (one 128-byte shared-memory row).  Per stage:
-//   * the weight tile B(q) (n_out x 128 B, pre-swizzled image) is streamed ONCE per group by a 1-D bulk async copy
-//     (TMA engine, mbarrier complete_tx) and reused by the T tiles of the group,
-//   * for each tile ONE producer warp gathers the A tile: it reads the tile's 128 neighbour indices (prefetched one
-//     stage ahead), ballots them, compacts the LIVE rows into a warp-private list of (source offset, swizzled
-//     destination) pairs and copies only those rows with 16-byte LDGSTS (8 lanes per 128-byte row).  The ballots are
-//     published as the stage's disable-output-lane mask.  The copies signal their landing themselves
-//     (cp.async.mbarrier.arrive.noinc), the warp never waits for them and alternates between its two A slots,
-//   * up to 4 issuing warps (tile t -> warp t mod NM) issue tcgen05.mma (M=128, N=n_out, K=16) with that mask:
-//     accumulator rows without a neighbour at this offset are not updated, so their stale A rows never reach a
-//     result.  Only the first stage of a tile, which initialises the accumulator, is written in full,
-//   * 4 epilogue warps drain finished accumulators (tcgen05.ld), add bias, convert and store.
-// Every output row is written exactly once: no atomics, deterministic.
+// EXPERIMENTAL, OFF BY DEFAULT (SCN_B200_STAGE_LISTS=1 turns it on in the Python layer): written after the round's GPU
+// budget was spent, compiled for sm_100a but not yet run on a GPU.  conv_tc.cu stays the validated product kernel and
+// is untouched by this file; tests/test_gpu_stage_lists.py holds the parity cases for this one.
 //
-// Synchronisation notes.  A slot's mbarriers must see consecutive phases from each waiter (a parity wait cannot tell
-// phase r from r-2), hence one producer warp per pair of slots; the issuing warps run up to SA stages apart, so the
-// "which stage is in this slot" handshake is a monotonically increasing sequence flag (release store / acquire poll)
-// and only then the landing barrier, whose parity the flag carries.
-//
-// What bounds it (timeline marks, -DSCN_TC_TIMELINE + tools/tc_timeline.py): neither L2 latency
-// nor the tensor pipe but the dependent-issue rate of the single warps that build a stage (~5 cycles per
-// instruction), so every role's per-stage instruction count was cut (6 instructions per gathered row segment,
-// ~70 per issued stage) and the roles were multiplied (5-6 producer warps, 4 issuing warps).
-// History (profiles/): dense zero-filled A tiles via cp.async, TMA tile::gather4 and lock-step LDG/STS batches
-// were measured first; they moved all 128 rows per stage although ~30% are live.
+// Same CTA organisation, pipelines and synchronisation as k_conv_tc (read its header first): persistent CTA per SM,
+// groups of T tiles in TMEM, 64-channel stages, bulk-copied weight tiles, LDGSTS row gather into SWIZZLE_128B A slots
+// that signal their own landing, masked tcgen05.mma issued by up to 4 warps, 4 epilogue warps.  What changes is the
+// producer warps' per-stage work, which bounds k_conv_tc at the shallow levels:
+//   * k_conv_tc builds every stage from the neighbour table: 128 (PAIR: 256) index loads, 4-8 ballots, prefix sums,
+//     list stores -- ~250 of the ~320 instructions a 32-channel stage costs its warp -- and every convolution that
+//     shares the rulebook (8 layers x forward + dgrad per level) repeats it;
+//   * here the list of a stage -- (source row, swizzled offset) per live row --, its length and its disable-lane mask
+//     come from the stage-list buffer built once per rulebook: the warp fetches a 24-byte header two stages ahead,
+//     starts ONE bulk async copy of the list (two in PAIR mode) one stage ahead into the other of its two list
+//     buffers, and when the A slot is free copies the mask words and issues the LDGSTS straight from the landed list;
+//   * the stage holding the CENTRE offset of the submanifold filter (every row is its own neighbour) is issued first
+//     and unmasked, so it initialises the accumulator and no stage is ever written in full or zero-filled; the other
+//     steps follow in ascending order (nat_step), and the weight loader fetches the image tiles in that order.
+//     PAIR mode (32 channels, two offsets per stage): the centre shares its stage with a neighbouring offset; that
+//     stage's MMAs start with the centre half (unmasked, accumulate = 0) and then issue the other half masked.
+// HBM: the lists are 8 bytes per (in,out) pair plus 24 bytes per stage instead of 4*K bytes per row of the table
+// (level 0 of the bench: ~54 instead of 108 bytes per row).
 //
 // Replaces SCN's dConvolution_KMxKN_forwardA/B; reference call sites
-// src/networks/sparse_building_blocks.py:29-34,110-117.
+// src/networks/sparse_building_blocks.py:29-34; src/networks/resnet.py:30-36,44-50.
 #include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
+#include "stage_lists.cuh"
 #include "tc_ptx.cuh"
 
-namespace tc {
+namespace tcl {
 
 constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
@@ -85,12 +80,16 @@ struct Params {
   int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
   unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
   int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 2 no MMAs
+  // stage lists of the table (stage_lists.cuh)
+  const unsigned char* lists;
+  int cstep;                    // step (offset, or offset pair in PAIR mode) that holds the centre offset: issued first
+  int chalf;                    // PAIR: half of that stage's 64 channels the centre offset occupies (0 lower, 1 upper)
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
 // 32 channels each (chunks 0-3 from offset 2q, chunks 4-7 from offset 2q+1), halving the stage count.
 template <int NCH, bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
+__global__ void __launch_bounds__(THREADS, 1) k_conv_tcl(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
@@ -106,12 +105,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   auto bempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + MAX_B + s); };
   auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + b); };
   auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 + b); };
-  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 4;          // 38 -> 304 bytes (a multiple of 16: amask stays 16-byte aligned)
+  constexpr int NBAR0 = 2 * MAX_A + 2 * MAX_B + 4;         // 38 -> 304 bytes (a multiple of 16: amask stays 16-byte aligned)
+  auto lbar = [&](int w, int b) { return bar0 + 8u * (uint32_t)(NBAR0 + 2 * w + b); };   // list landed in buffer b of warp w
+  constexpr int NBAR = NBAR0 + 2 * PROD_WARPS;                                            // 50 -> 400 bytes
+  constexpr int LIST_WARP_BYTES = (PAIR ? 2 : 1) * LIST_BYTES * 2;                        // two list buffers per warp
   unsigned char* tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + 8 * NBAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   uint32_t* amask = reinterpret_cast<uint32_t*>(tail + 16);                    // [MAX_A][8], 16-byte aligned
   unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][LIST_BYTES]
-  const uint32_t aseq = smem_u32(lists + PROD_WARPS * (PAIR ? 2 : 1) * LIST_BYTES);             // [MAX_A] u32: stage number + 1 in slot
+  const uint32_t aseq = smem_u32(lists + PROD_WARPS * LIST_WARP_BYTES);                         // [MAX_A] u32: stage number + 1 in slot
 
   // warp index through a broadcast shuffle: the compiler then knows it is warp-uniform (role branches, barrier
   // addresses and slot numbers stay in uniform registers instead of per-lane copies with R2UR waterfalls)
@@ -142,6 +144,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         mbar_init(accf(b), p.NM);
         mbar_init(acce(b), EPI_WARPS);
       }
+      for (int w = 0; w < PROD_WARPS; ++w)
+        for (int b = 0; b < 2; ++b) mbar_init(lbar(w, b), 1);     // the issuing lane's expect_tx arrival (+ complete_tx bytes)
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -164,35 +168,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   auto tiles_in_group = [&](int g) { return my_tiles - g * T < T ? my_tiles - g * T : T; };
   const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // offsets (offset pairs) per tile
   const int Q = NSTEP * NCH;                                // stages per tile
+  // stage order: the centre step first, the others in ascending order
+  auto nat_step = [&](int step) { return step == 0 ? p.cstep : (step <= p.cstep ? step - 1 : step); };
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // ================================ A producers (warp pw <-> A slot pw) ====================
     // NPW = SA/2 warps are active; warp pw owns A slots pw and pw + NPW and alternates between them (stage n -> warp
     // n mod NPW, slot n mod SA), so a slot has one producer and its mbarrier sees consecutive phases (parity-safe).
     // A single warp issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count IS the
-    // gather throughput: the list holds ready-made (source row, swizzled destination address) pairs, and an item
-    // costs one LDS.64, one IMAD.WIDE, one LOP3 and one 16-byte LDGSTS per lane.  The copies are asynchronous: the
-    // warp builds and issues its next stage (other slot) while this one is in flight, then waits, fences and publishes.
+    // gather throughput: the landed list holds ready-made (source row, swizzled offset) pairs, and an item costs one
+    // LDS.64, one IMAD.WIDE, one LOP3 + IADD and one 16-byte LDGSTS per lane.  Everything else about a stage -- its
+    // header (two stages ahead) and its list (one stage ahead) -- is in flight while the previous stages are issued.
     const int pw = warp - EPI_WARPS;
     const int NPW = SA >> 1;
     if (pw < NPW) {
       constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
       constexpr int IPP = 32 / LPI;                        // items per pass
       const int chunk = lane % LPI, sub = lane / LPI;
-      int2* list = reinterpret_cast<int2*>(lists + pw * (PAIR ? 2 : 1) * LIST_BYTES);   // .x source row offset / 16 B (-1: zeros), .y smem address
-      const uint32_t row_vec = (uint32_t)p.n_in >> 3;      // 16-byte units per feature row (list offsets are in these units)
+      int2* list = reinterpret_cast<int2*>(lists + pw * LIST_WARP_BYTES);   // this warp's two list buffers (.x source row, .y offset in the slot)
       const int last_chunks = p.last_kc >> 3;
-      const uint32_t lt = (1u << lane) - 1u;
       const uint32_t csw = (uint32_t)chunk << 4;
-      const uint32_t slot_stride = (uint32_t)NPW * A_BYTES;
       const int total = my_tiles * Q;                      // stages of this CTA, in MMA order (group, stage, tile)
-      // swizzled address of (row 32i + lane, 16-byte chunk 0) in slot pw (upper half, PAIR: ^ 0x40; other slot: + stride)
-      uint32_t dlo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t r = 32u * i + lane;
-        dlo[i] = a_base + (uint32_t)pw * A_BYTES + (r << 7) + ((r & 7u) << 4);
-      }
 
       // stage cursor (tile t of stage q of group g)
       int t = 0, q = 0, g = 0;
@@ -205,102 +201,113 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         }
       };
       advance(t, q, g, pw);
-      // neighbour indices of a stage: lane l holds rows l, 32+l, 64+l, 96+l of the tile (PAIR: of both offsets)
-      auto load_idx = [&](int t_, int q_, int g_, int (&jl)[4], int (&jh)[4]) {
-        const int step = PAIR ? q_ : q_ / NCH;
-        const int64_t tile = (int64_t)tile_lo + (int64_t)g_ * T + t_;
-        const int k0 = PAIR ? 2 * step : step;
-        const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + lane;
-        const bool hi_ok = PAIR && (k0 + 1 < p.K);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          jl[i] = ldg_nc32(src + 32 * i);
-          jh[i] = hi_ok ? ldg_nc32(src + p.n_pad + 32 * i) : -1;
+      {
+        // ---------------- precomputed stage lists ----------------
+        const int2* hdr = reinterpret_cast<const int2*>(p.lists + sl::hdr_offset());
+        const uint32_t* msk = reinterpret_cast<const uint32_t*>(p.lists + sl::msk_offset(p.num_tiles, p.K));
+        const unsigned char* ent = p.lists + sl::ent_offset(p.num_tiles, p.K);
+        if (pw == 0 && lane == 0) {                        // the buffer was built for this table shape
+          const uint32_t* head = reinterpret_cast<const uint32_t*>(p.lists);
+          if (head[1] != (uint32_t)p.K || head[2] != (uint32_t)p.num_tiles || head[3] != sl::MAGIC) __trap();
         }
-      };
-
-      int jl[4], jh[4];
-      if (pw < total) load_idx(t, q, g, jl, jh);
-      int it = 0;
-      for (int n = pw; n < total; n += NPW, ++it) {
-        const int slot = pw + (it & 1) * NPW;
-        const uint32_t soff = (it & 1) ? slot_stride : 0u;
-        mark(0, n, 0);
-        const int cc = PAIR ? 0 : q % NCH;
-        const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
-        // ---- live rows -> list (full stage: every row, missing ones as zeros) --------------------------------
-        uint32_t B[4], H[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          B[i] = __ballot_sync(0xffffffffu, jl[i] >= 0);
-          H[i] = PAIR ? __ballot_sync(0xffffffffu, jh[i] >= 0) : 0u;
-        }
-        int nlive = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pos = full ? 32 * i + lane : nlive + __popc(B[i] & lt);
-          if (full || jl[i] >= 0) list[pos] = make_int2(jl[i] >= 0 ? (int)((uint32_t)jl[i] * row_vec) : -1, (int)(dlo[i] + soff));
-          nlive += full ? 32 : __popc(B[i]);
-        }
-        if (PAIR) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int pos = full ? 128 + 32 * i + lane : nlive + __popc(H[i] & lt);
-            if (full || jh[i] >= 0) list[pos] = make_int2(jh[i] >= 0 ? (int)((uint32_t)jh[i] * row_vec) : -1, (int)((dlo[i] + soff) ^ 0x40u));
-            nlive += full ? 32 : __popc(H[i]);
+        const uint32_t row_bytes = (uint32_t)p.n_in * 2u;
+        const uint32_t lbuf_u32 = smem_u32(list);          // buffer b: + b * LIST_WARP_BYTES / 2; PAIR second list: + LIST_BYTES
+        constexpr uint32_t LBUF = LIST_WARP_BYTES / 2;
+        struct Hd { int off0, cnt0, off1, cnt1, cc; uint32_t mword; };
+        // header of the stage under the cursor: where its list(s) are, how long, its mask words (lanes 0..7), its chunk
+        auto load_hd = [&](int t_, int q_, int g_) {
+          Hd h;
+          const int step = PAIR ? q_ : q_ / NCH;
+          const int ns = nat_step(step);
+          const int64_t tile = (int64_t)tile_lo + (int64_t)g_ * T + t_;
+          const int k0 = PAIR ? 2 * ns : ns;
+          const bool has1 = PAIR && (k0 + 1 < p.K);
+          const size_t s0 = (size_t)tile * (size_t)p.K + (size_t)k0;
+          const int2 a = __ldg(hdr + s0);
+          int2 b = make_int2(0, 0);
+          if (has1) b = __ldg(hdr + s0 + 1);
+          h.off0 = a.x; h.cnt0 = a.y; h.off1 = b.x; h.cnt1 = b.y;
+          h.cc = PAIR ? 0 : q_ % NCH;
+          h.mword = 0xffffffffu;
+          if (lane < 4) h.mword = __ldg(msk + s0 * 4 + lane);
+          else if (lane < 8 && has1) h.mword = __ldg(msk + (s0 + 1) * 4 + (lane - 4));
+          return h;
+        };
+        // one bulk copy per list into buffer b of this warp; the copy engine signals lbar itself
+        auto issue_list = [&](int b, const Hd& h) {
+          const uint32_t bytes0 = (uint32_t)h.cnt0 * 8u, bytes1 = PAIR ? (uint32_t)h.cnt1 * 8u : 0u;   // counts are multiples of 8 entries
+          if (elect_one()) {
+            mbar_expect_tx(lbar(pw, b), bytes0 + bytes1);
+            const uint32_t dst = lbuf_u32 + (uint32_t)b * LBUF;
+            if (bytes0) bulk_g2s(dst, ent + (size_t)(uint32_t)h.off0 * 8u, bytes0, lbar(pw, b));
+            if (bytes1) bulk_g2s(dst + LIST_BYTES, ent + (size_t)(uint32_t)h.off1 * 8u, bytes1, lbar(pw, b));
           }
+          __syncwarp();
+        };
+        Hd hA = {0, 0, 0, 0, 0, 0xffffffffu}, hB = hA;
+        if (pw < total) {
+          hA = load_hd(t, q, g);
+          issue_list(0, hA);
         }
-        __syncwarp();
-        uint32_t mword = 0;                                // lanes 0..7: the 8 words of the slot's lane masks
-        if (lane < 8) {
-          const uint32_t lo = (lane & 2) ? ((lane & 1) ? B[3] : B[2]) : ((lane & 1) ? B[1] : B[0]);
-          const uint32_t hi = (lane & 2) ? ((lane & 1) ? H[3] : H[2]) : ((lane & 1) ? H[1] : H[0]);
-          mword = ~(lane < 4 ? lo : hi);
-        }
-        mark(0, n, 1);
-        // prefetch the next stage's indices (consumed in the next iteration)
         advance(t, q, g, NPW);
-        if (n + NPW < total) load_idx(t, q, g, jl, jh);
-
-        // the MMAs that read this slot's previous stage (two iterations ago) have retired
-        mbar_wait(aempty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);
-        if (lane < 8) amask[slot * 8 + lane] = mword;
-        mark(0, n, 2);
-        const int npass = (nlive + IPP - 1) / IPP;
-        const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
-        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
-        if (lane_on) {
-          if (!full) {
-            // hot path, ~6 instructions per item: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
-            for (int p0 = 0; p0 < npass; p0 += 6) {        // 6 list entries are read before their copies are issued
-              int2 e[6];
+        if (pw + NPW < total) hB = load_hd(t, q, g);
+        int it = 0;
+        for (int n = pw; n < total; n += NPW, ++it) {
+          const int slot = pw + (it & 1) * NPW;
+          const uint32_t slot_base = a_base + (uint32_t)slot * A_BYTES;
+          mark(0, n, 0);
+          // the next stage's list -> the other buffer (last read two iterations ago, before that iteration's __syncwarp)
+          if (n + NPW < total) issue_list((it + 1) & 1, hB);
+          // header of the stage after that (in flight while this stage is issued)
+          Hd hC = hB;
+          advance(t, q, g, NPW);
+          if (n + 2 * NPW < total) hC = load_hd(t, q, g);
+          mark(0, n, 1);
+          // the MMAs that read this slot's previous stage (two iterations ago) have retired
+          mbar_wait(aempty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);
+          if (lane < 8) amask[slot * 8 + lane] = hA.mword;
+          // this stage's list has landed
+          mbar_wait(lbar(pw, it & 1), ((uint32_t)it >> 1) & 1u);
+          mark(0, n, 2);
+          const bool lane_on = PAIR ? true : chunk < (hA.cc == NCH - 1 ? last_chunks : 8);
+          const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)hA.cc * 128u + csw);
+          if (lane_on) {
+            // Lists are whole groups of 8 entries (padded by repeating the last one), so there is no per-item predicate:
+            // an item costs LDS.64, IMAD.WIDE (source), LOP3 + IADD (destination) and the 16-byte LDGSTS.
+            auto copy = [&](const int2 e, uint32_t cx) {
+              cp_async16(slot_base + ((uint32_t)e.y ^ cx), src0 + (uint64_t)(uint32_t)e.x * (uint64_t)row_bytes, 16u);
+            };
 #pragma unroll
-              for (int u = 0; u < 6; ++u) {
-                const int item = (p0 + u) * IPP + sub;
-                e[u] = make_int2(0, 0);
-                if (item < nlive) e[u] = list[item];
+            for (int half = 0; half < (PAIR ? 2 : 1); ++half) {
+              const int cnt = half ? hA.cnt1 : hA.cnt0;
+              const int2* L = reinterpret_cast<const int2*>(reinterpret_cast<const unsigned char*>(list) +
+                                                            (size_t)(it & 1) * LBUF + (size_t)half * LIST_BYTES) + sub;
+              const uint32_t cx = half ? (csw ^ 0x40u) : csw;
+              if constexpr (PAIR) {                        // 8 items per pass: 16 entries per iteration, one pass may remain
+                int i = 0;
+                for (; i + 8 < cnt; i += 16) {
+                  const int2 e0 = L[i], e1 = L[i + 8];
+                  copy(e0, cx);
+                  copy(e1, cx);
+                }
+                if (i < cnt) copy(L[i], cx);
+              } else {                                     // 4 items per pass: 8 entries = two passes per iteration
+                for (int i = 0; i < cnt; i += 8) {
+                  const int2 e0 = L[i], e1 = L[i + 4];
+                  copy(e0, cx);
+                  copy(e1, cx);
+                }
               }
-#pragma unroll
-              for (int u = 0; u < 6; ++u)
-                if (e[u].y != 0) cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(uint32_t)e[u].x << 4), 16u);
-            }
-          } else {
-            // first stage of a tile: every row is written, missing neighbours as zeros (src-size 0 reads nothing)
-            for (int pass = 0; pass < npass; ++pass) {
-              const int2 e = list[pass * IPP + sub];
-              const bool live = e.x != -1;
-              cp_async16((uint32_t)e.y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e.x : 0u) << 4), live ? 16u : 0u);
             }
           }
+          cp_async_arrive_noinc(afull(slot));
+          __syncwarp();                                    // all lanes have read the list buffer (refilled next iteration)
+          if (lane == 0)
+            st_release_u32(aseq + 4u * (uint32_t)slot, ((uint32_t)n + 1u) | ((((uint32_t)it >> 1) & 1u) << 31));
+          mark(0, n, 3);
+          hA = hB;
+          hB = hC;
         }
-        // Landing is signalled by the copies themselves: every lane's arrival on afull(slot) fires when its cp.async
-        // have completed.  The sequence flag only tells the issuing warps WHICH stage the slot now holds (and the
-        // parity of the landing phase to wait for); the producer never waits for its own copies.
-        cp_async_arrive_noinc(afull(slot));
-        __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
-        if (lane == 0)
-          st_release_u32(aseq + 4u * (uint32_t)slot, ((uint32_t)n + 1u) | ((((uint32_t)it >> 1) & 1u) << 31));
-        mark(0, n, 3);
       }
     }
   } else if (warp == WARP_BLOAD) {
@@ -316,7 +323,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       mark(2, i, 1);
       if (elect_one()) {
         mbar_expect_tx(bfull(bslot), b_bytes);
-        bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)(i % Q) * b_bytes, b_bytes, bfull(bslot));
+        int bq = i % Q;                                  // image tile of the stage (the image is in natural step order)
+        bq = PAIR ? nat_step(bq) : nat_step(bq / NCH) * NCH + bq % NCH;
+        bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)bq * b_bytes, b_bytes, bfull(bslot));
       }
       __syncwarp();
       if (++bslot == SB) { bslot = 0; ++bround; }
@@ -349,7 +358,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
           mark(3, g * Q + q, 1);
           const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
           // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
-          const int nk = (p.exp & 2) ? 0 : (PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4));
+          const int nk = (p.exp & 2) ? 0 : (PAIR ? ((2 * nat_step(step) + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4));
+          // PAIR, first stage: the half that holds the centre offset is unmasked and issued first (it
+          // initialises the accumulator), the other half is an ordinary masked offset
+          const bool first_pair = PAIR && q == 0;
           int t = m;
           for (; t < tv; t += NM) {
             mark(1, (int)seq - 1, 0);
@@ -366,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
             // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
             // them provably warp-uniform so they are moved to uniform registers once.
             uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-            if (q > 0) {
+            if (q > 0 || first_pair) {
               const uint4 mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
               m0 = __ballot_sync(0xffffffffu, (mw.x >> lane) & 1u);
               m1 = __ballot_sync(0xffffffffu, (mw.y >> lane) & 1u);
@@ -380,14 +392,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
                 h3 = __ballot_sync(0xffffffffu, (hw.w >> lane) & 1u);
               }
             }
+            if (first_pair) {
+              if (p.chalf) { h0 = 0; h1 = 0; h2 = 0; h3 = 0; }
+              else { m0 = 0; m1 = 0; m2 = 0; m3 = 0; }
+            }
             const uint64_t da = da0 + (uint64_t)((uint32_t)aslot * (A_BYTES >> 4));
             const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 if (kk < nk) {
-                  const bool hi = PAIR && kk >= 2;
-                  umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
+                  const int kx = (first_pair && p.chalf) ? (kk ^ 2) : kk;      // K16 slice of the stage this MMA reads
+                  const bool hi = PAIR && kx >= 2;
+                  umma_masked(tmem_d, da + (uint64_t)(kx * 2), db + (uint64_t)(kx * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
                               hi ? h0 : m0, hi ? h1 : m1, hi ? h2 : m2, hi ? h3 : m3);
                 }
               }
@@ -459,144 +476,75 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   }
 }
 
-// Weight image: one tile per stage q = k*nch + c/64: n_out rows of 128 bytes; the 16-byte chunk (c%64)/8 of row n
-// is stored at chunk position chunk ^ (n & 7) (the SWIZZLE_128B pattern); unused half rows stay zero.
-__global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, int Cout, int transpose, int mirror,
-                                  int nch, int pair, __nv_bfloat16* __restrict__ img) {
-  const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
-  int64_t total = (int64_t)K * n_in * n_out;
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int k = (int)(i / ((int64_t)n_in * n_out));
-  int rem = (int)(i - (int64_t)k * n_in * n_out);
-  int n = rem / n_in, c = rem % n_in;
-  int src_k = (transpose && mirror) ? K - 1 - k : k;
-  int ci = transpose ? n : c, co = transpose ? c : n;
-  float v = W[((int64_t)src_k * Cin + ci) * Cout + co];
-  // pair (n_in == 32): stage q = k/2, chunks 0-3 <- offset 2q, chunks 4-7 <- offset 2q+1
-  const int q = pair ? (k >> 1) : k * nch + c / KC;
-  const int chunk = pair ? (k & 1) * 4 + (c >> 3) : (c % KC) >> 3;
-  size_t off = ((size_t)q * n_out + n) * 64 + (size_t)((chunk ^ (n & 7)) << 3) + (c & 7);
-  img[off] = __float2bfloat16_rn(v);
-}
+}  // namespace tcl
 
-}  // namespace tc
+static bool tcl_pair(int n_in) { return n_in == 32; }
 
-// Debug: device buffer of 4 roles x 256 stages x 8 marks (uint64) filled by CTA 0 of the following launches; NULL disables.
-static unsigned long long* g_tc_dbg = nullptr;
-extern "C" void scn_tc_debug_timeline(void* device_buffer) { g_tc_dbg = (unsigned long long*)device_buffer; }
-
-bool scn_tc_disabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("SCN_B200_DISABLE_TC");
-    v = (e && e[0] && e[0] != '0') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-bool scn_tc_shape_ok(int K, int n_in, int n_out) {
-  return K >= 1 && (n_in % 32) == 0 && (n_out % 32) == 0 && n_in >= 32 && n_in <= 256 && n_out >= 32 && n_out <= 256;
-}
-
-// n_in == 32: two offsets share a 64-channel stage
-static bool tc_pair(int n_in) { return n_in == 32; }
-
-size_t scn_tc_image_bytes(int K, int n_in, int n_out) {
-  const size_t stages = tc_pair(n_in) ? (size_t)(K + 1) / 2 : (size_t)K * ((n_in + tc::KC - 1) / tc::KC);
-  return stages * n_out * 128;
-}
-
-int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s) {
-  const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
-  const int nch = (n_in + tc::KC - 1) / tc::KC;
-  if ((n_in % tc::KC) != 0) SCN_CUDA(cudaMemsetAsync(out, 0, scn_tc_image_bytes(K, n_in, n_out), s));
-  int64_t total = (int64_t)K * Cin * Cout;
-  tc::k_prep_weights_tc<<<grid_for(total, 256), 256, 0, s>>>(W, K, Cin, Cout, transpose, mirror, nch,
-                                                             tc_pair(n_in) ? 1 : 0, (__nv_bfloat16*)out);
-  SCN_LAUNCH_CHECK();
-  return SCN_OK;
-}
-
-// conv_tcl.cu: the same convolution driven by precomputed stage lists (experimental, opt-in)
+// Launched by scn_tc_forward (conv_tc.cu) when the caller passed the stage lists of a submanifold table
+// (K odd, centre offset = identity, n_rows == n_in_rows).  Same tile / ring sizing as k_conv_tc.
 int scn_tcl_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                     int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
-                    const void* lists, unsigned long long* dbg, int exp_flags, cudaStream_t s);
-
-// lists: stage lists of the table (stage_lists.cuh) or null; only a SUBMANIFOLD table (K odd, centre offset =
-// identity, n_rows == n_in_rows) may come with lists, and the call is then routed to k_conv_tcl.
-int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
-                   int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
-                   const void* lists, cudaStream_t s) {
-  if ((uint64_t)n_in_rows * (uint64_t)(n_in >> 3) >= 0xffffffffull) return SCN_ERR_UNSUPPORTED;   // 32-bit offsets in 16-byte units (64 GB)
-  tc::Params p;
-  {
-    static int exp_flags = -1;
-    if (exp_flags < 0) {
-      const char* e = std::getenv("SCN_B200_TC_EXP");
-      exp_flags = e ? std::atoi(e) : 0;
-    }
-    p.exp = exp_flags;
-  }
-  if (lists != nullptr && (K & 1) == 1 && n_rows == n_in_rows && n_pad == (n_rows + tc::BM - 1) / tc::BM * tc::BM)
-    return scn_tcl_forward(in, n_in_rows, nbr, K, n_rows, n_pad, n_in, n_out, bimg, bias, out, lists, g_tc_dbg, p.exp, s);
-  p.dbg = g_tc_dbg;
+                    const void* lists, unsigned long long* dbg, int exp_flags, cudaStream_t s) {
+  if (!lists || (K & 1) == 0 || n_rows != n_in_rows) return SCN_ERR_ARG;
+  if ((uint64_t)n_in_rows * (uint64_t)n_in * 2ull >= (1ull << 40)) return SCN_ERR_UNSUPPORTED;
+  tcl::Params p;
+  p.exp = exp_flags;
+  p.dbg = dbg;
+  p.lists = (const unsigned char*)lists;
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
-  const int nch = (n_in + tc::KC - 1) / tc::KC;
-  p.last_kc = n_in - (nch - 1) * tc::KC;
-  p.num_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-  // tiles per group: as many accumulators as fit in half of TMEM (weight-tile reuse, and one issuing warp per
-  // tile up to MMA_WARPS); the tiles themselves are split evenly over the CTAs, so T does not unbalance the grid
+  const int nch = (n_in + tcl::KC - 1) / tcl::KC;
+  p.last_kc = n_in - (nch - 1) * tcl::KC;
+  p.num_tiles = (int)((n_rows + tcl::BM - 1) / tcl::BM);
   int T = 256 / n_out;
   if (T < 1) T = 1;
   if (T > 8) T = 8;
   p.nbuf = 2;
   const int per_cta = (p.num_tiles + kNumSMs - 1) / kNumSMs;
   {
-    // One group in all 512 TMEM columns instead of two alternating halves: the epilogue then no longer overlaps the
-    // next group's MMAs, but T doubles (more issuing warps, more weight-tile reuse).  Worth it when a CTA has a
-    // single group anyway, or when half of TMEM holds one tile only.
     int t1 = 512 / n_out;
     if (t1 > 8) t1 = 8;
     if (t1 > T && (per_cta <= t1 || T == 1)) { T = t1; p.nbuf = 1; }
   }
   if (T > per_cta) T = per_cta;
   p.T = T;
-  p.NM = T < tc::MMA_WARPS ? T : tc::MMA_WARPS;
+  p.NM = T < tcl::MMA_WARPS ? T : tcl::MMA_WARPS;
   p.num_groups = 0;
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
-  // weight ring: up to 4 tiles (3 in flight behind the one being consumed), within ~72 KB
   {
     int sb = (int)((72u * 1024u) / b_bytes);
-    if (sb > tc::MAX_B) sb = tc::MAX_B;
+    if (sb > tcl::MAX_B) sb = tcl::MAX_B;
     if (sb < 2) sb = 2;
     p.SB = sb;
   }
-  const bool pair = tc_pair(n_in);
-  constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 4;
-  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + 8u * NBAR + 16u + (uint32_t)tc::MAX_A * tc::MASK_BYTES +
-                         (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES * (pair ? 2u : 1u) + 4u * tc::MAX_A + 12u;
+  const bool pair = tcl_pair(n_in);
+  const int c = (K - 1) / 2;                     // centre offset of the (odd) filter
+  p.cstep = pair ? (c >> 1) : c;
+  p.chalf = pair ? (c & 1) : 0;
+  // mirrors the kernel's carve-up (two mbarriers and two list buffers per producer warp more than k_conv_tc)
+  constexpr int NBAR = 2 * tcl::MAX_A + 2 * tcl::MAX_B + 4 + 2 * tcl::PROD_WARPS;
+  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + 8u * NBAR + 16u + (uint32_t)tcl::MAX_A * tcl::MASK_BYTES +
+                         (uint32_t)tcl::PROD_WARPS * tcl::LIST_BYTES * (pair ? 2u : 1u) * 2u + 4u * tcl::MAX_A + 12u;
   const uint32_t budget = 226u * 1024u;
-  int SA = (int)((budget - fixed) / tc::A_BYTES);
-  if (SA > tc::MAX_A) SA = tc::MAX_A;
+  int SA = (int)((budget - fixed) / tcl::A_BYTES);
+  if (SA > tcl::MAX_A) SA = tcl::MAX_A;
   SA &= ~1;                                      // two A slots per producer warp
   if (SA < 4) return SCN_ERR_UNSUPPORTED;
   p.SA = SA;
-  size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
+  size_t smem = (size_t)fixed + (size_t)SA * tcl::A_BYTES;
   int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
   auto launch = [&](auto kern) -> int {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, tc::THREADS, smem, s>>>(p);
+    kern<<<grid, tcl::THREADS, smem, s>>>(p);
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };
-  if (pair) return launch(tc::k_conv_tc<1, true>);
+  if (pair) return launch(tcl::k_conv_tcl<1, true>);
   switch (nch) {
-    case 1: return launch(tc::k_conv_tc<1, false>);
-    case 2: return launch(tc::k_conv_tc<2, false>);
-    case 3: return launch(tc::k_conv_tc<3, false>);
-    case 4: return launch(tc::k_conv_tc<4, false>);
+    case 1: return launch(tcl::k_conv_tcl<1, false>);
+    case 2: return launch(tcl::k_conv_tcl<2, false>);
+    case 3: return launch(tcl::k_conv_tcl<3, false>);
+    case 4: return launch(tcl::k_conv_tcl<4, false>);
     default: return SCN_ERR_UNSUPPORTED;
   }
 }

@@ -60,76 +60,100 @@ class ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner=None):
-        x = x.contiguous()
-        prec = config.precision_code()
-        fdt = config.feature_dtype()
-        K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
-        fat = (owner is not None and not ops.profiling() and weight.dtype == torch.float32 and weight.is_contiguous()
-               and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous())))
-        ctx.fat = fat
-        if fat:
-            ws = owner.workspace(K, cin, cout, prec, fdt, x.device)
-            if ws.path > 0 and x.dtype != fdt:
-                x = ops.convert(x, fdt)
-            # always re-laid: fused optimizers update parameters without bumping Tensor._version (see modules._conv)
-            out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False)
-            ctx.ws = ws
-        else:
-            w3 = _w3(weight)
-            bprep = ops.prep_weights(w3, False, False, prec, fdt)
-            b = bias.detach().float().contiguous() if bias is not None else None
-            out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, fdt)
-        ctx.save_for_backward(x, weight, bias)
-        ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.prec = nbr_fwd, nbr_bwd, mirror, prec
-        ctx.n_out_rows = n_out_rows
-        return out
+        return _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, None)
 
     @staticmethod
     def backward(ctx, dout):
-        x, weight, bias = ctx.saved_tensors
-        dout = dout.contiguous()
-        K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
-        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        need_db = bias is not None and ctx.needs_input_grad[2]
-        dx = dw = db = None
-        if ctx.fat:
-            ws = ctx.ws
-            xw = x
-            if ws.path > 0 and x.dtype != dout.dtype:
-                xw = ops.convert(x, dout.dtype)
-            # parameter gradients: straight into .grad when the trainer asked for it, else into fresh buffers
-            gw = _direct_grad(weight) if need_dw else None
-            gb = _direct_grad(bias) if need_db else None
-            if need_dw and gw is None:
-                dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
-            if need_db and gb is None:
-                db = torch.empty(bias.shape, dtype=torch.float32, device=x.device)
-            wimg_t, skip = None, False
-            if need_dx:
-                wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
-                skip = False
-            dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
-                                          ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
-                                          gw if gw is not None else dw, gw is None,
-                                          gb if gb is not None else db, gb is not None)
-            if dx is not None and dx.dtype != x.dtype:
-                dx = ops.convert(dx, x.dtype)
-            if gw is not None:
-                _grad_ready(weight)
-            if gb is not None:
-                _grad_ready(bias)
-            return dx, dw, db, None, None, None, None, None
+        return _conv_backward(ctx, dout) + (None,) * 5
+
+
+class ConvSlFn(Function):
+    """ConvFn with the stage lists of a submanifold table (nbr_fwd is nbr_bwd): the experimental k_conv_tcl path
+    (csrc/conv_tcl.cu), used by SubmanifoldConvolution when SCN_B200_STAGE_LISTS=1."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists):
+        return _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists)
+
+    @staticmethod
+    def backward(ctx, dout):
+        return _conv_backward(ctx, dout) + (None,) * 6
+
+
+def _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists):
+    x = x.contiguous()
+    ctx.lists = lists
+    prec = config.precision_code()
+    fdt = config.feature_dtype()
+    K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
+    fat = (owner is not None and not ops.profiling() and weight.dtype == torch.float32 and weight.is_contiguous()
+           and (bias is None or (bias.dtype == torch.float32 and bias.is_contiguous())))
+    ctx.fat = fat
+    if fat:
+        ws = owner.workspace(K, cin, cout, prec, fdt, x.device)
+        if ws.path > 0 and x.dtype != fdt:
+            x = ops.convert(x, fdt)
+        # always re-laid: fused optimizers update parameters without bumping Tensor._version (see modules._conv)
+        out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False,
+                                      lists=lists)
+        ctx.ws = ws
+    else:
         w3 = _w3(weight)
+        bprep = ops.prep_weights(w3, False, False, prec, fdt)
+        b = bias.detach().float().contiguous() if bias is not None else None
+        out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, fdt, lists=lists)
+    ctx.save_for_backward(x, weight, bias)
+    ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.prec = nbr_fwd, nbr_bwd, mirror, prec
+    ctx.n_out_rows = n_out_rows
+    return out
+
+
+def _conv_backward(ctx, dout):
+    """-> (dx, dw, db)"""
+    x, weight, bias = ctx.saved_tensors
+    dout = dout.contiguous()
+    K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
+    need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+    need_db = bias is not None and ctx.needs_input_grad[2]
+    dx = dw = db = None
+    if ctx.fat:
+        ws = ctx.ws
+        xw = x
+        if ws.path > 0 and x.dtype != dout.dtype:
+            xw = ops.convert(x, dout.dtype)
+        # parameter gradients: straight into .grad when the trainer asked for it, else into fresh buffers
+        gw = _direct_grad(weight) if need_dw else None
+        gb = _direct_grad(bias) if need_db else None
+        if need_dw and gw is None:
+            dw = torch.empty(weight.shape, dtype=torch.float32, device=x.device)
+        if need_db and gb is None:
+            db = torch.empty(bias.shape, dtype=torch.float32, device=x.device)
+        wimg_t, skip = None, False
         if need_dx:
-            bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec, x.dtype)
-            dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
-                                  kind="conv_dgrad")
-        if need_dw:
-            dw = ops.conv_wgrad(x, dout, ctx.nbr_fwd, ctx.n_out_rows, cin, cout, ctx.prec).view_as(weight)
-            dw = dw.to(weight.dtype)
-        if need_db:
-            db = ops.col_sum(dout)
-        return dx, dw, db, None, None, None, None, None
+            wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
+            skip = False
+        dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
+                                      ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
+                                      gw if gw is not None else dw, gw is None,
+                                      gb if gb is not None else db, gb is not None, lists_bwd=ctx.lists)
+        if dx is not None and dx.dtype != x.dtype:
+            dx = ops.convert(dx, x.dtype)
+        if gw is not None:
+            _grad_ready(weight)
+        if gb is not None:
+            _grad_ready(bias)
+        return dx, dw, db
+    w3 = _w3(weight)
+    if need_dx:
+        bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec, x.dtype)
+        dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
+                              kind="conv_dgrad", lists=ctx.lists)
+    if need_dw:
+        dw = ops.conv_wgrad(x, dout, ctx.nbr_fwd, ctx.n_out_rows, cin, cout, ctx.prec).view_as(weight)
+        dw = dw.to(weight.dtype)
+    if need_db:
+        db = ops.col_sum(dout)
+    return dx, dw, db
 
 
 class BatchNormFn(Function):
