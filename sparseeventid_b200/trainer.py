@@ -116,6 +116,42 @@ def warmup_flat_lr(step: int, peak: float = 3e-3, warmup_steps: int = 100) -> fl
     return peak
 
 
+# ------------------------------------------------------------------------------------------------
+# Checkpoints in the reference's (pytorch_lightning) layout: {"state_dict": {"encoder....", "head...."}, ...}.
+# src/utils/create_trainer.py:83-115: ModelCheckpoint every 50 steps; restore = the whole module, or with
+# mode.restore_encoder_only the encoder alone (keys containing "encoder", prefix stripped) which is then FROZEN.
+# ------------------------------------------------------------------------------------------------
+
+
+def checkpoint_dict(model: torch.nn.Module, optimizer=None, scheduler=None, global_step: int = 0) -> dict:
+    """The subset of a Lightning checkpoint the reference reads back (+ optimizer / scheduler state, Lightning names)."""
+    ck = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "global_step": int(global_step)}
+    if optimizer is not None:
+        ck["optimizer_states"] = [optimizer.state_dict()]
+    if scheduler is not None:
+        ck["lr_schedulers"] = [scheduler.state_dict()]
+    return ck
+
+
+def restore_checkpoint(model: torch.nn.Module, checkpoint: dict, encoder_only: bool = False, optimizer=None,
+                       scheduler=None) -> int:
+    """Loads a Lightning-layout checkpoint (this repo's or the reference's) into `model`; returns its global step.
+    encoder_only mirrors create_trainer.py:94-106: only the encoder's tensors are loaded and the encoder is frozen."""
+    sd = checkpoint["state_dict"]
+    if encoder_only:
+        enc = {k.replace("encoder.", ""): v for k, v in sd.items() if "encoder" in k}
+        model.encoder.load_state_dict(enc)
+        for p in model.encoder.parameters():
+            p.requires_grad = False
+        return int(checkpoint.get("global_step", 0))
+    model.load_state_dict(sd)
+    if optimizer is not None and checkpoint.get("optimizer_states"):
+        optimizer.load_state_dict(checkpoint["optimizer_states"][0])
+    if scheduler is not None and checkpoint.get("lr_schedulers"):
+        scheduler.load_state_dict(checkpoint["lr_schedulers"][0])
+    return int(checkpoint.get("global_step", 0))
+
+
 class Trainer:
     def __init__(self, scn, dataset: str = "dune3d", device="cuda", cfg: Optional[networks.EncoderConfig] = None,
                  seed: int = 0, weight_decay: float = 1e-6, peak_lr: float = 3e-3, fused_adam: Optional[bool] = None):
@@ -133,7 +169,26 @@ class Trainer:
         self.opt = torch.optim.Adam(self.model.parameters(), lr=1.0, eps=1e-6, betas=(0.8, 0.9),
                                     weight_decay=weight_decay, fused=fused_adam)
         self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: warmup_flat_lr(s, peak_lr))
+        self.peak_lr = peak_lr
+        self.global_step = 0
         self.model.train()
+
+    def save_checkpoint(self, path: str) -> None:
+        """Lightning-layout checkpoint (rank 0 writes under data parallelism: every rank holds the same state)."""
+        if not self.distributed or dist.get_rank() == 0:
+            torch.save(checkpoint_dict(self.model, self.opt, self.sched, self.global_step), path)
+
+    def load_checkpoint(self, path: str, encoder_only: bool = False) -> None:
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        self.global_step = restore_checkpoint(self.model, ck, encoder_only, None if encoder_only else self.opt,
+                                              None if encoder_only else self.sched)
+        if encoder_only:      # frozen parameters leave the optimizer and the gradient arena
+            live = [p for p in self.model.parameters() if p.requires_grad]
+            self.arena = FlatGradArena(live)
+            self.opt = torch.optim.Adam(live, lr=1.0, eps=1e-6, betas=(0.8, 0.9),
+                                        weight_decay=self.opt.param_groups[0]["weight_decay"],
+                                        fused=self.opt.param_groups[0].get("fused") or False)
+            self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lambda s: warmup_flat_lr(s, self.peak_lr))
 
     def prefetch_rulebooks(self, next_batch, ready_event=None):
         """Has the rulebooks of the NEXT batch built on the rulebook stream now (they depend on coordinates only), so
@@ -160,4 +215,5 @@ class Trainer:
         self.arena.finish()
         self.opt.step()
         self.sched.step()
+        self.global_step += 1
         return loss
