@@ -507,6 +507,22 @@ int scn_tcl_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* n
     if (t1 > T && (per_cta <= t1 || T == 1)) { T = t1; p.nbuf = 1; }
   }
   if (T > per_cta) T = per_cta;
+  {
+    // developer knob (sweeps of weight-tile re-streaming vs epilogue overlap): SCN_B200_TC_T=<tiles per group>
+    static int force_t = -1;
+    if (force_t < 0) {
+      const char* e = std::getenv("SCN_B200_TC_T");
+      force_t = e ? std::atoi(e) : 0;
+    }
+    if (force_t > 0) {
+      T = force_t;
+      if (T > 8) T = 8;
+      if (T * n_out > 512) T = 512 / n_out;
+      if (T > per_cta) T = per_cta;
+      if (T < 1) T = 1;
+      p.nbuf = T * n_out <= 256 ? 2 : 1;
+    }
+  }
   p.T = T;
   p.NM = T < tcl::MMA_WARPS ? T : tcl::MMA_WARPS;
   p.num_groups = 0;
