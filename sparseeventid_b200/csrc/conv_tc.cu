@@ -552,7 +552,17 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   if (T < 1) T = 1;
   if (T > 8) T = 8;
   p.nbuf = 2;
-  const int per_cta = (p.num_tiles + kNumSMs - 1) / kNumSMs;
+  int max_ctas = kNumSMs;
+  {
+    // developer knob: SCN_B200_TC_GRID=<CTAs> caps the grid (fewer CTAs, more tiles per group: less weight re-streaming)
+    static int force_grid = -1;
+    if (force_grid < 0) {
+      const char* e = std::getenv("SCN_B200_TC_GRID");
+      force_grid = e ? std::atoi(e) : 0;
+    }
+    if (force_grid > 0 && force_grid < max_ctas) max_ctas = force_grid;
+  }
+  const int per_cta = (p.num_tiles + max_ctas - 1) / max_ctas;
   {
     // One group in all 512 TMEM columns instead of two alternating halves: the epilogue then no longer overlaps the
     // next group's MMAs, but T doubles (more issuing warps, more weight-tile reuse).  Worth it when a CTA has a
@@ -600,7 +610,7 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   if (SA < 4) return SCN_ERR_UNSUPPORTED;
   p.SA = SA;
   size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
-  int grid = p.num_tiles < kNumSMs ? p.num_tiles : kNumSMs;
+  int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
   auto launch = [&](auto kern) -> int {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, tc::THREADS, smem, s>>>(p);

@@ -20,3 +20,4 @@ step "bench default" bash -c 'timeout 300 python bench.py --no-cpu-baseline > gp
 step "bench stage lists" bash -c 'SCN_B200_STAGE_LISTS=1 timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_stage_lists.json && tail -c 1500 gpurun_out/bench_stage_lists.json'
 # 5. weight re-streaming: tiles per group forced up (single TMEM buffer) at the levels where weights dominate L2 traffic
 step "T sweep" bash -c 'for t in 2 3 4 5; do echo "SCN_B200_TC_T=$t"; for a in "154605 27 96 96" "59700 27 128 128" "20727 27 160 160" "7332 27 192 192"; do SCN_B200_TC_T=$t timeout 60 python tools/tc_profile.py $a 5; done; done'
+step "grid sweep (deep levels: fewer CTAs x more tiles per group)" bash -c 'for g in 37 74 111; do for t in 2 3; do echo "SCN_B200_TC_GRID=$g SCN_B200_TC_T=$t"; for a in "20727 27 160 160" "7332 27 192 192"; do SCN_B200_TC_GRID=$g SCN_B200_TC_T=$t timeout 60 python tools/tc_profile.py $a 5; done; done; done'
