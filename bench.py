@@ -373,6 +373,15 @@ def run_ours(args, rank, world, local_rank):
                     "achieved_algorithmic_gbs": by / t / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
                     "frac_of_hbm": by / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["_source"],
                     "share_of_step": sum(r["ms"] for r in tc) / 2 / (ms / args.steps)}
+            try:
+                # per launch the binding roof is max(flops / tensor peak, algorithmic bytes / HBM peak): at these widths
+                # (arithmetic intensity below the 207 FLOP/B ridge) it is usually the HBM one
+                t_roof = sum(max(conv_algorithmic(r, eb)[0] / (peak * 1e12), conv_algorithmic(r, eb)[1] / (peaks["hbm_gbs"] * 1e9))
+                             for r in tc)
+                roof["time_at_binding_roof_ms_per_step"] = t_roof * 1e3 / 2
+                roof["frac_of_binding_roof"] = t_roof / t
+            except Exception:                       # never let a derived figure cost the bench line
+                pass
         breakdown = {k: {"ms_per_step": v["ms"] / 2, "launches_per_step": v["launches"] / 2,
                          "tflops": (v["flops"] / (v["ms"] * 1e-3) / 1e12) if v["flops"] and v["ms"] else None,
                          "algorithmic_gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["bytes"] and v["ms"] else None}
