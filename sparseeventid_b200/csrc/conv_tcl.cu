@@ -271,6 +271,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tcl(const Params p) {
           mark(0, n, 2);
           const bool lane_on = PAIR ? true : chunk < (hA.cc == NCH - 1 ? last_chunks : 8);
           const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)hA.cc * 128u + csw);
+          // keep the whole base in one register pair: otherwise the compiler leaves p.in in a uniform register and
+          // adds it to every item's address (IADD3 + IADD3.X per item on top of the IMAD.WIDE)
+          asm volatile("" : "+l"(src0));
           if (lane_on) {
             // Lists are whole groups of 8 entries (padded by repeating the last one), so there is no per-item predicate:
             // an item costs LDS.64, IMAD.WIDE (source), LOP3 + IADD (destination) and the 16-byte LDGSTS.
