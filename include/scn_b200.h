@@ -160,23 +160,6 @@ int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows, const int3
                      int64_t n_out_rows, int64_t n_pad, int n_in, int n_out, const void* Bprep,
                      const float* bias, int precision, void* out, int out_dtype, void* stream);
 
-/* ------------------------------------------------------------------------------------------
- * Stage lists of a SUBMANIFOLD neighbour table (optional; csrc/stage_lists.cuh): per (128-row tile,
- * offset) the live rows compacted into ready-made gather items, the count and the disable-lane mask
- * -- the per-stage work of the tcgen05 convolution's gathering warps, done once per rulebook and
- * reused by every convolution that shares it (SCN caches its rulebooks per Metadata the same way).
- * scn_stage_lists_bytes: size of the buffer (upper bound); scn_stage_lists_build fills it.
- * The *_sl entry points are the plain ones with one more argument: the lists of the table they
- * gather through (nbr for forward, nbr_bwd for the backward's dgrad), or NULL.
- * ------------------------------------------------------------------------------------------ */
-size_t scn_stage_lists_bytes(int K, int64_t n_pad);
-int scn_stage_lists_build(const int32_t* nbr, int K, int64_t n_pad, void* lists, size_t lists_bytes,
-                          void* stream);
-int scn_conv_forward_sl(const void* in, int in_dtype, int64_t n_in_rows, const int32_t* nbr, int K,
-                        int64_t n_out_rows, int64_t n_pad, int n_in, int n_out, const void* Bprep,
-                        const float* bias, int precision, void* out, int out_dtype,
-                        const void* stage_lists, void* stream);
-
 /* dW: fp32 [K][n_in][n_out], ACCUMULATED into (caller zeroes); `in` rows are gathered through
  * nbr (the SAME table the forward used), dout rows are the table's own rows [n_rows, n_out]. */
 int scn_conv_wgrad(const void* in, int in_dtype, const void* dout, int dout_dtype,
@@ -211,19 +194,6 @@ int scn_conv_module_backward(const void* x, int x_dtype, int64_t n_in_rows, cons
                              int Cin, int Cout, const float* W, int mirror, int precision,
                              void* wimg_t, int skip_prep, void* dx, float* dW, int zero_dW,
                              float* dbias, int accumulate_dbias, double* stats_ws, void* stream);
-
-int scn_conv_module_forward_sl(const void* x, int x_dtype, int64_t n_in_rows, const int32_t* nbr,
-                               int K, int64_t n_out_rows, int64_t n_pad, int Cin, int Cout,
-                               const float* W, const float* bias, int precision, void* wimg,
-                               int skip_prep, void* out, int out_dtype, const void* stage_lists,
-                               void* stream);
-int scn_conv_module_backward_sl(const void* x, int x_dtype, int64_t n_in_rows, const void* dout,
-                                int dout_dtype, int64_t n_out_rows, const int32_t* nbr_fwd,
-                                int64_t n_pad_fwd, const int32_t* nbr_bwd, int64_t n_pad_bwd, int K,
-                                int Cin, int Cout, const float* W, int mirror, int precision,
-                                void* wimg_t, int skip_prep, void* dx, float* dW, int zero_dW,
-                                float* dbias, int accumulate_dbias, double* stats_ws,
-                                const void* stage_lists_bwd, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Bandwidth-bound layers.  Feature matrices are [n, C] row-major of `dtype`.

@@ -48,13 +48,6 @@ SIGNATURES = {
     "scn_conv_module_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "scn_conv_module_backward": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p, _i, _i, _p, _i,
                                       _p, _p, _i, _p, _i, _p, _p]),
-    # the same three with one more pointer before the stream: the stage lists of the table they gather through
-    "scn_conv_forward_sl": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p, _p]),
-    "scn_conv_module_forward_sl": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p, _p]),
-    "scn_conv_module_backward_sl": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p, _i, _i, _p, _i,
-                                         _p, _p, _i, _p, _i, _p, _p, _p]),
-    "scn_stage_lists_bytes": (_sz, [_i, _i64]),
-    "scn_stage_lists_build": (_i, [_p, _i, _i64, _p, _sz, _p]),
     "scn_bn_forward": (_i, [_p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p]),
     "scn_leaky_forward": (_i, [_p, _i, _i64, _f, _p, _p]),

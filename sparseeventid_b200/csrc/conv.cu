@@ -16,7 +16,7 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
                  int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s);
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
-                   const void* lists, cudaStream_t s);
+                   cudaStream_t s);
 
 namespace {
 
@@ -560,21 +560,13 @@ extern "C" int scn_conv_prep_weights(const float* W, int K, int Cin, int Cout, i
 extern "C" int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows, const int32_t* nbr, int K,
                                 int64_t n_out_rows, int64_t n_pad, int n_in, int n_out, const void* Bprep,
                                 const float* bias, int precision, void* out, int out_dtype, void* stream) {
-  return scn_conv_forward_sl(in, in_dtype, n_in_rows, nbr, K, n_out_rows, n_pad, n_in, n_out, Bprep, bias, precision, out,
-                             out_dtype, nullptr, stream);
-}
-
-extern "C" int scn_conv_forward_sl(const void* in, int in_dtype, int64_t n_in_rows, const int32_t* nbr, int K,
-                                   int64_t n_out_rows, int64_t n_pad, int n_in, int n_out, const void* Bprep,
-                                   const float* bias, int precision, void* out, int out_dtype, const void* stage_lists,
-                                   void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (n_out_rows == 0) return SCN_OK;
   if (!in || !nbr || !Bprep || !out || K < 1 || n_pad < n_out_rows || (n_pad & 127)) return SCN_ERR_ARG;
   if (precision == SCN_PREC_FP32 && (in_dtype != SCN_F32 || out_dtype != SCN_F32)) return SCN_ERR_ARG;
   if (in_dtype == out_dtype && conv_path(K, n_in, n_out, precision, in_dtype) == 2)
     return scn_tc_forward((const __nv_bfloat16*)in, n_in_rows, nbr, K, n_out_rows, n_pad, n_in, n_out, Bprep, bias,
-                          (__nv_bfloat16*)out, stage_lists, s);
+                          (__nv_bfloat16*)out, s);
   if (mma_ok(K, n_in, n_out, precision) && in_dtype == out_dtype) {
     if (in_dtype == SCN_F32)
       return conv_mma_t<float>((const float*)in, nbr, K, n_out_rows, n_pad, n_in, n_out, (const __nv_bfloat16*)Bprep,

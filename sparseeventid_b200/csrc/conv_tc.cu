@@ -44,14 +44,15 @@ constexpr int BM = 128;                 // output rows per tile == TMEM lanes
 constexpr int KC = 64;                  // channels per pipeline stage (one 128-byte swizzle row)
 constexpr int A_BYTES = BM * 128;       // 16 KB
 constexpr int EPI_WARPS = 4;            // warps 0..3  (TMEM lane quarter = warp index)
-constexpr int PROD_WARPS = 6;           // warps 4..9; the first SA/2 of them are active, two A slots each
+constexpr int NGRP = 4;                 // producer groups: stage n is gathered by group n mod NGRP ...
+constexpr int PROD_WARPS = 4 * NGRP;    // ... whose 4 warps own one 32-row quarter of the tile each (warps 4..19)
 constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS;   // first of MMA_WARPS issuing warps (tile t -> warp t mod NM)
 constexpr int MMA_WARPS = 4;
 constexpr int WARP_BLOAD = WARP_MMA + MMA_WARPS;   // weight tiles
-constexpr int THREADS = 32 * (WARP_BLOAD + 1);
-constexpr int MAX_A = 2 * PROD_WARPS, MAX_B = 6;   // ring depths: A tiles, B tiles
+constexpr int THREADS = 32 * (WARP_BLOAD + 1);     // 800
+constexpr int MAX_A = 12, MAX_B = 8;    // ring depths: A tiles (a multiple of NGRP), B tiles
 constexpr int MASK_BYTES = 32;          // per A slot: 2 x 128-bit disable-output-lane masks (second: PAIR upper half)
-constexpr int LIST_BYTES = 128 * 8;     // per producer warp: live items of its stage, (source row, smem address); x2 in PAIR mode
+constexpr int LIST_BYTES = 64 * 8;      // per producer warp: live items of its quarter stage, (source row, smem address)
 using namespace tcptx;
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
@@ -79,12 +80,11 @@ struct Params {
   int K, n_in, n_out;
   int last_kc;                  // channels in the last 64-channel chunk of an offset (64 or 32)
   int T;                        // tiles per group
-  int SA, SB;                   // A / B ring depth (SA == number of active producer warps)
-  int num_tiles, num_groups;
+  int SA, SB;                   // A / B ring depth
+  int num_tiles;
   int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
   int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
   unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
-  int exp;                      // SCN_B200_TC_EXP timing experiments (WRONG results): 2 no MMAs
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
@@ -106,12 +106,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   auto bempty = [&](int s) { return bar0 + 8u * (uint32_t)(2 * MAX_A + MAX_B + s); };
   auto accf = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + b); };
   auto acce = [&](int b) { return bar0 + 8u * (uint32_t)(2 * MAX_A + 2 * MAX_B + 2 + b); };
-  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 4;          // 38 -> 304 bytes (a multiple of 16: amask stays 16-byte aligned)
+  constexpr int NBAR = 2 * MAX_A + 2 * MAX_B + 4;          // 44 -> 352 bytes (a multiple of 16: amask stays 16-byte aligned)
   unsigned char* tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + 8 * NBAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   uint32_t* amask = reinterpret_cast<uint32_t*>(tail + 16);                    // [MAX_A][8], 16-byte aligned
   unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][LIST_BYTES]
-  const uint32_t aseq = smem_u32(lists + PROD_WARPS * (PAIR ? 2 : 1) * LIST_BYTES);             // [MAX_A] u32: stage number + 1 in slot
 
   // warp index through a broadcast shuffle: the compiler then knows it is warp-uniform (role branches, barrier
   // addresses and slot numbers stay in uniform registers instead of per-lane copies with R2UR waterfalls)
@@ -130,8 +129,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) {
-        st_release_u32(aseq + 4u * (uint32_t)s, 0u);
-        mbar_init(afull(s), 32);                  // the 32 lanes of the owning producer warp, each when its copies landed
+        mbar_init(afull(s), 132);                 // the 4 x 32 lanes of the stage's producer group, each when its copies landed, + 4 mask publications
         mbar_init(aempty(s), 1);                  // one tcgen05.commit
       }
       for (int s = 0; s < SB; ++s) {
@@ -165,143 +163,132 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // offsets (offset pairs) per tile
   const int Q = NSTEP * NCH;                                // stages per tile
 
+  // Classes: tile t of a group belongs to class t mod NM (NM = 1, 2 or 4).  A class is an independent pipeline: ONE issuing
+  // warp, NGRP / NM producer groups and a private ring of SA / NM A slots.  Every slot therefore has a single consumer
+  // and its producers see consecutive phases, so plain parity mbarriers are safe (no sequence flags, no fences).
+  const int NM = p.NM;
+  const int spc = SA / NM;                                  // A slots per class (a multiple of NGRP / NM)
+
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
-    // ================================ A producers (warp pw <-> A slot pw) ====================
-    // NPW = SA/2 warps are active; warp pw owns A slots pw and pw + NPW and alternates between them (stage n -> warp
-    // n mod NPW, slot n mod SA), so a slot has one producer and its mbarrier sees consecutive phases (parity-safe).
-    // A single warp issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count IS the
-    // gather throughput: the list holds ready-made (source row, swizzled destination address) pairs, and an item
-    // costs one LDS.64, one IMAD.WIDE, one LOP3 and one 16-byte LDGSTS per lane.  The copies are asynchronous: the
-    // warp builds and issues its next stage (other slot) while this one is in flight, then waits, fences and publishes.
+    // ================================ A producers ============================================
+    // Group grp serves class grp mod NM as sub-worker grp / NM: it gathers every (NGRP / NM)-th stage of the class, in
+    // the class's MMA order (group, stage, tile).  Warp wq of the group owns rows 32 wq .. 32 wq + 31 of the tile: ONE
+    // neighbour index per lane, one ballot, one 32-bit word of the stage's disable-output-lane mask.  A single warp
+    // issues roughly one dependent instruction per 5 cycles, so the per-stage instruction count of a warp IS its
+    // gather rate: a quarter stage costs ~100 instructions (the 128-row stages of the first version of this kernel:
+    // ~470), and 16 warps work at once.  Live rows are compacted into a warp-private list of (source row, swizzled
+    // destination) items so that every 16-byte LDGSTS pass moves 4 whole rows (8 lanes per 128-byte row; PAIR: 8 half
+    // rows).  The copies signal their landing themselves (cp.async.mbarrier.arrive.noinc); the warp never waits for
+    // them, and nothing in the loop is a memory fence (a MEMBAR would wait for the copies in flight).
     const int pw = warp - EPI_WARPS;
-    const int NPW = SA >> 1;
-    if (pw < NPW) {
-      constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
-      constexpr int IPP = 32 / LPI;                        // items per pass
-      const int chunk = lane % LPI, sub = lane / LPI;
-      int2* list = reinterpret_cast<int2*>(lists + pw * (PAIR ? 2 : 1) * LIST_BYTES);   // .x source row offset / 16 B (-1: zeros), .y smem address
-      const uint32_t row_vec = (uint32_t)p.n_in >> 3;      // 16-byte units per feature row (list offsets are in these units)
-      const int last_chunks = p.last_kc >> 3;
-      const uint32_t lt = (1u << lane) - 1u;
-      const uint32_t csw = (uint32_t)chunk << 4;
-      const uint32_t slot_stride = (uint32_t)NPW * A_BYTES;
-      const int total = my_tiles * Q;                      // stages of this CTA, in MMA order (group, stage, tile)
-      // swizzled address of (row 32i + lane, 16-byte chunk 0) in slot pw (upper half, PAIR: ^ 0x40; other slot: + stride)
-      uint32_t dlo[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t r = 32u * i + lane;
-        dlo[i] = a_base + (uint32_t)pw * A_BYTES + (r << 7) + ((r & 7u) << 4);
+    const int grp = pw >> 2, wq = pw & 3;
+    const int cls = grp % NM, sub = grp / NM, gpc = NGRP / NM;
+    constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
+    constexpr int IPP = 32 / LPI;                        // items per pass
+    const int chunk = lane % LPI, isub = lane / LPI;
+    int2* list = reinterpret_cast<int2*>(lists + pw * LIST_BYTES);   // .x source row offset / 16 B (-1: zeros), .y smem address
+    const uint32_t row_vec = (uint32_t)p.n_in >> 3;      // 16-byte units per feature row (list offsets are in these units)
+    const int last_chunks = p.last_kc >> 3;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t csw = (uint32_t)chunk << 4;
+    // swizzled address of (row 32 wq + lane, 16-byte chunk 0) in slot 0 (upper half, PAIR: ^ 0x40)
+    const uint32_t myrow = 32u * (uint32_t)wq + (uint32_t)lane;
+    const uint32_t drow = a_base + (myrow << 7) + ((myrow & 7u) << 4);
+
+    // cursor over the class's stages: tile t (= cls, cls + NM, ...) of stage q of group g
+    int t = cls, q = 0, g = 0, tv = my_groups > 0 ? tiles_in_group(0) : 0;
+    auto step = [&]() {
+      t += NM;
+      if (t >= tv) {
+        t = cls;
+        if (++q == Q) { q = 0; ++g; tv = g < my_groups ? tiles_in_group(g) : 0; }
       }
+    };
+    // only the last group of a CTA can be partial: once the class has no tile in a group it has no stage left
+    auto valid = [&]() { return g < my_groups && cls < tv; };
+    for (int i = 0; i < sub; ++i)
+      if (valid()) step();
+    // neighbour index of this lane's row for a stage (PAIR: of both offsets)
+    auto load_idx = [&](int& jl, int& jh) {
+      const int stp = PAIR ? q : q / NCH;
+      const int64_t tile = (int64_t)tile_lo + (int64_t)g * T + t;
+      const int k0 = PAIR ? 2 * stp : stp;
+      const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + myrow;
+      jl = ldg_nc32(src);
+      jh = (PAIR && (k0 + 1 < p.K)) ? ldg_nc32(src + p.n_pad) : -1;
+    };
 
-      // stage cursor (tile t of stage q of group g)
-      int t = 0, q = 0, g = 0;
-      auto advance = [&](int& t_, int& q_, int& g_, int by) {
-        t_ += by;
-        int tv = tiles_in_group(g_);
-        while (t_ >= tv && g_ < my_groups) {
-          t_ -= tv;
-          if (++q_ == Q) { q_ = 0; ++g_; tv = tiles_in_group(g_); }
-        }
-      };
-      advance(t, q, g, pw);
-      // neighbour indices of a stage: lane l holds rows l, 32+l, 64+l, 96+l of the tile (PAIR: of both offsets)
-      auto load_idx = [&](int t_, int q_, int g_, int (&jl)[4], int (&jh)[4]) {
-        const int step = PAIR ? q_ : q_ / NCH;
-        const int64_t tile = (int64_t)tile_lo + (int64_t)g_ * T + t_;
-        const int k0 = PAIR ? 2 * step : step;
-        const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + lane;
-        const bool hi_ok = PAIR && (k0 + 1 < p.K);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          jl[i] = ldg_nc32(src + 32 * i);
-          jh[i] = hi_ok ? ldg_nc32(src + p.n_pad + 32 * i) : -1;
-        }
-      };
-
-      int jl[4], jh[4];
-      if (pw < total) load_idx(t, q, g, jl, jh);
-      int it = 0;
-      for (int n = pw; n < total; n += NPW, ++it) {
-        const int slot = pw + (it & 1) * NPW;
-        const uint32_t soff = (it & 1) ? slot_stride : 0u;
-        mark(0, n, 0);
-        const int cc = PAIR ? 0 : q % NCH;
-        const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
-        // ---- live rows -> list (full stage: every row, missing ones as zeros) --------------------------------
-        uint32_t B[4], H[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          B[i] = __ballot_sync(0xffffffffu, jl[i] >= 0);
-          H[i] = PAIR ? __ballot_sync(0xffffffffu, jh[i] >= 0) : 0u;
-        }
-        int nlive = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int pos = full ? 32 * i + lane : nlive + __popc(B[i] & lt);
-          if (full || jl[i] >= 0) list[pos] = make_int2(jl[i] >= 0 ? (int)((uint32_t)jl[i] * row_vec) : -1, (int)(dlo[i] + soff));
-          nlive += full ? 32 : __popc(B[i]);
-        }
+    int jl = -1, jh = -1;
+    if (valid()) load_idx(jl, jh);
+    int ls = sub;                                        // slot within the class ring (sub < gpc <= spc)
+    uint32_t round = 0;
+    while (valid()) {
+      const int slot = cls * spc + ls;
+      const int cc = PAIR ? 0 : q % NCH;
+      const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
+      const uint32_t dst = drow + (uint32_t)slot * A_BYTES;
+      // ---- live rows -> list (full stage: every row, missing ones as zeros) ----------------------------------
+      const uint32_t bl = __ballot_sync(0xffffffffu, jl >= 0);
+      const uint32_t bh = PAIR ? __ballot_sync(0xffffffffu, jh >= 0) : 0u;
+      int nlive;
+      if (full) {
+        list[lane] = make_int2(jl >= 0 ? (int)((uint32_t)jl * row_vec) : -1, (int)dst);
+        if (PAIR) list[32 + lane] = make_int2(jh >= 0 ? (int)((uint32_t)jh * row_vec) : -1, (int)(dst ^ 0x40u));
+        nlive = PAIR ? 64 : 32;
+      } else {
+        if (jl >= 0) list[__popc(bl & lt)] = make_int2((int)((uint32_t)jl * row_vec), (int)dst);
+        nlive = __popc(bl);
         if (PAIR) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int pos = full ? 128 + 32 * i + lane : nlive + __popc(H[i] & lt);
-            if (full || jh[i] >= 0) list[pos] = make_int2(jh[i] >= 0 ? (int)((uint32_t)jh[i] * row_vec) : -1, (int)((dlo[i] + soff) ^ 0x40u));
-            nlive += full ? 32 : __popc(H[i]);
-          }
+          if (jh >= 0) list[nlive + __popc(bh & lt)] = make_int2((int)((uint32_t)jh * row_vec), (int)(dst ^ 0x40u));
+          nlive += __popc(bh);
         }
-        __syncwarp();
-        uint32_t mword = 0;                                // lanes 0..7: the 8 words of the slot's lane masks
-        if (lane < 8) {
-          const uint32_t lo = (lane & 2) ? ((lane & 1) ? B[3] : B[2]) : ((lane & 1) ? B[1] : B[0]);
-          const uint32_t hi = (lane & 2) ? ((lane & 1) ? H[3] : H[2]) : ((lane & 1) ? H[1] : H[0]);
-          mword = ~(lane < 4 ? lo : hi);
-        }
-        mark(0, n, 1);
-        // prefetch the next stage's indices (consumed in the next iteration)
-        advance(t, q, g, NPW);
-        if (n + NPW < total) load_idx(t, q, g, jl, jh);
-
-        // the MMAs that read this slot's previous stage (two iterations ago) have retired
-        mbar_wait(aempty(slot), (((uint32_t)it >> 1) & 1u) ^ 1u);
-        if (lane < 8) amask[slot * 8 + lane] = mword;
-        mark(0, n, 2);
-        const int npass = (nlive + IPP - 1) / IPP;
-        const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
-        const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
-        if (lane_on) {
-          if (!full) {
-            // hot path, ~6 instructions per item: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
-            for (int p0 = 0; p0 < npass; p0 += 6) {        // 6 list entries are read before their copies are issued
-              int2 e[6];
-#pragma unroll
-              for (int u = 0; u < 6; ++u) {
-                const int item = (p0 + u) * IPP + sub;
-                e[u] = make_int2(0, 0);
-                if (item < nlive) e[u] = list[item];
-              }
-#pragma unroll
-              for (int u = 0; u < 6; ++u)
-                if (e[u].y != 0) cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(uint32_t)e[u].x << 4), 16u);
-            }
-          } else {
-            // first stage of a tile: every row is written, missing neighbours as zeros (src-size 0 reads nothing)
-            for (int pass = 0; pass < npass; ++pass) {
-              const int2 e = list[pass * IPP + sub];
-              const bool live = e.x != -1;
-              cp_async16((uint32_t)e.y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e.x : 0u) << 4), live ? 16u : 0u);
-            }
-          }
-        }
-        // Landing is signalled by the copies themselves: every lane's arrival on afull(slot) fires when its cp.async
-        // have completed.  The sequence flag only tells the issuing warps WHICH stage the slot now holds (and the
-        // parity of the landing phase to wait for); the producer never waits for its own copies.
-        cp_async_arrive_noinc(afull(slot));
-        __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
-        if (lane == 0)
-          st_release_u32(aseq + 4u * (uint32_t)slot, ((uint32_t)n + 1u) | ((((uint32_t)it >> 1) & 1u) << 31));
-        mark(0, n, 3);
       }
+      __syncwarp();
+      // prefetch the next stage's indices (consumed in the next iteration)
+      for (int i = 0; i < gpc; ++i) step();
+      if (valid()) load_idx(jl, jh);
+
+      // the MMAs that read this slot's previous stage have retired
+      mbar_wait(aempty(slot), (round & 1u) ^ 1u);
+      if (lane == 0) {
+        amask[slot * 8 + wq] = ~bl;
+        if (PAIR) amask[slot * 8 + 4 + wq] = ~bh;
+      }
+      const int npass = (nlive + IPP - 1) / IPP;         // <= 8
+      const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
+      const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
+      if (lane_on) {
+        if (!full) {
+          // hot path per pass: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
+          for (int p0 = 0; p0 < npass; p0 += 4) {        // 4 list entries are read before their copies are issued
+            int2 e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int item = (p0 + u) * IPP + isub;
+              e[u] = make_int2(0, 0);
+              if (item < nlive) e[u] = list[item];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (e[u].y != 0) cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(uint32_t)e[u].x << 4), 16u);
+          }
+        } else {
+          // first stage of a tile: every row is written, missing neighbours as zeros (src-size 0 reads nothing)
+#pragma unroll
+          for (int pass = 0; pass < 8; ++pass) {
+            const int2 e = list[pass * IPP + isub];
+            const bool live = e.x != -1;
+            cp_async16((uint32_t)e.y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e.x : 0u) << 4), live ? 16u : 0u);
+          }
+        }
+      }
+      // Landing is signalled by the copies themselves: every lane's arrival on afull(slot) fires when its cp.async
+      // have completed.  Lane 0's ordinary arrival (release) publishes the mask words it stored above.
+      cp_async_arrive_noinc(afull(slot));
+      if (lane == 0) mbar_arrive(afull(slot));
+      __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
+      ls += gpc;
+      if (ls >= spc) { ls -= spc; ++round; }
     }
   } else if (warp == WARP_BLOAD) {
     // ================================ weight-tile loader (1 elected lane, bulk async copies) ==
@@ -325,16 +312,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     // ================================ MMA issuers (warp-uniform loops, 1 elected lane issues) =
     // The per-stage issue path (two mbarrier waits, mask fetch, 4 UTCHMMA, commit) costs one warp several hundred
     // cycles, more than the tensor pipe needs for the stage, so the T tiles of a group (independent accumulators)
-    // are dealt to NM = min(T, 4) issuing warps: warp m issues tiles m, m + NM, ...
-    const int m = warp - WARP_MMA, NM = p.NM;
+    // are dealt to NM = 1, 2 or 4 issuing warps (classes): warp m issues tiles m, m + NM, ...
+    const int m = warp - WARP_MMA;                                    // == class
     if (m < NM) {
       const uint32_t idesc = make_idesc(p.n_out);
       const uint64_t da0 = make_desc_sw128(a_base), db0 = make_desc_sw128(b_base);
       const int nbuf = p.nbuf;
       int bslot = 0;
       uint32_t bround = 0;
-      int aslot = m % SA;                                             // slot of this warp's next stage (n mod SA), kept incrementally
-      uint32_t seq = (uint32_t)m + 1u;                                // its sequence number (n + 1)
+      int ls = 0;                                                     // this class's next stage: slot m * spc + ls ...
+      uint32_t around = 0;                                            // ... in round `around` of that slot
       for (int g = 0; g < my_groups; ++g) {
         const int buf = nbuf == 2 ? (g & 1) : 0;
         const uint32_t use = (uint32_t)(nbuf == 2 ? (g >> 1) : g);    // how many times this buffer has been used before
@@ -349,20 +336,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
           mark(3, g * Q + q, 1);
           const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
           // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
-          const int nk = (p.exp & 2) ? 0 : (PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4));
-          int t = m;
-          for (; t < tv; t += NM) {
-            mark(1, (int)seq - 1, 0);
-            {
-              uint32_t spins = 0, f;
-              while (((f = ld_acquire_u32(aseq + 4u * (uint32_t)aslot)) & 0x7fffffffu) != seq)   // slot holds stage n?
-                if (++spins > SPIN_LIMIT) __trap();
-              __syncwarp();
-              mbar_wait(afull(aslot), f >> 31);              // ... and its rows have landed (phase parity from the flag)
-            }
-            mark(1, (int)seq - 1, 1);
+          const int nk = PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4);
+          for (int t = m; t < tv; t += NM) {
+            const int aslot = m * spc + ls;
+            mbar_wait(afull(aslot), around & 1u);            // all four quarters of the stage have landed (and their masks)
             tc_fence_after();
-            // disable-output-lane masks published by the stage's producer: bit r set <=> output row r has no
+            // disable-output-lane masks published by the stage's producers: bit r set <=> output row r has no
             // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
             // them provably warp-uniform so they are moved to uniform registers once.
             uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
@@ -394,18 +373,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
               umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
             }
             __syncwarp();
-            mark(1, (int)seq - 1, 2);
-            aslot += NM; if (aslot >= SA) aslot -= SA;                 // NM <= 4 <= SA
-            seq += (uint32_t)NM;
-          }
-          // this warp's next stage is tile m of the next q (or group): skip the tiles of other warps in between
-          {
-            const int adv = tv - t + m;                                // stages from (q, t) to (q + 1, m): tv - t + m, may be negative
-            int a2 = aslot + adv;
-            while (a2 < 0) a2 += SA;
-            while (a2 >= SA) a2 -= SA;
-            aslot = a2;
-            seq = (uint32_t)((int)seq + adv);
+            if (++ls == spc) { ls = 0; ++around; }
           }
           if (elect_one()) umma_commit(bempty(bslot));
           __syncwarp();
@@ -518,28 +486,28 @@ int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mir
   return SCN_OK;
 }
 
-// conv_tcl.cu: the same convolution driven by precomputed stage lists (experimental, opt-in)
-int scn_tcl_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
-                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
-                    const void* lists, unsigned long long* dbg, int exp_flags, cudaStream_t s);
+// developer knobs for sweeps (read once): SCN_B200_TC_GRID caps the CTAs, SCN_B200_TC_T forces the tiles per group,
+// SCN_B200_TC_SA / SCN_B200_TC_SB force the A / B ring depths
+static int env_int(const char* name) {
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) : 0;
+}
+static int g_knob[4] = {-1, -1, -1, -1};      // grid, T, SA, SB: -1 = read the environment on first use
+// developer entry for the sweep tools (like scn_tc_debug_timeline: not part of the product ABI): 0 = automatic
+extern "C" void scn_tc_debug_knobs(int grid, int t, int sa, int sb) {
+  g_knob[0] = grid; g_knob[1] = t; g_knob[2] = sa; g_knob[3] = sb;
+}
 
-// lists: stage lists of the table (stage_lists.cuh) or null; only a SUBMANIFOLD table (K odd, centre offset =
-// identity, n_rows == n_in_rows) may come with lists, and the call is then routed to k_conv_tcl.
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
                    int64_t n_pad, int n_in, int n_out, const void* bimg, const float* bias, __nv_bfloat16* out,
-                   const void* lists, cudaStream_t s) {
+                   cudaStream_t s) {
   if ((uint64_t)n_in_rows * (uint64_t)(n_in >> 3) >= 0xffffffffull) return SCN_ERR_UNSUPPORTED;   // 32-bit offsets in 16-byte units (64 GB)
-  tc::Params p;
-  {
-    static int exp_flags = -1;
-    if (exp_flags < 0) {
-      const char* e = std::getenv("SCN_B200_TC_EXP");
-      exp_flags = e ? std::atoi(e) : 0;
-    }
-    p.exp = exp_flags;
+  if (g_knob[0] < 0) {
+    g_knob[0] = env_int("SCN_B200_TC_GRID"); g_knob[1] = env_int("SCN_B200_TC_T");
+    g_knob[2] = env_int("SCN_B200_TC_SA"); g_knob[3] = env_int("SCN_B200_TC_SB");
   }
-  if (lists != nullptr && (K & 1) == 1 && n_rows == n_in_rows && n_pad == (n_rows + tc::BM - 1) / tc::BM * tc::BM)
-    return scn_tcl_forward(in, n_in_rows, nbr, K, n_rows, n_pad, n_in, n_out, bimg, bias, out, lists, g_tc_dbg, p.exp, s);
+  const int force_grid = g_knob[0], force_t = g_knob[1], force_sa = g_knob[2], force_sb = g_knob[3];
+  tc::Params p;
   p.dbg = g_tc_dbg;
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
@@ -553,66 +521,62 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   if (T > 8) T = 8;
   p.nbuf = 2;
   int max_ctas = kNumSMs;
-  {
-    // developer knob: SCN_B200_TC_GRID=<CTAs> caps the grid (fewer CTAs, more tiles per group: less weight re-streaming)
-    static int force_grid = -1;
-    if (force_grid < 0) {
-      const char* e = std::getenv("SCN_B200_TC_GRID");
-      force_grid = e ? std::atoi(e) : 0;
-    }
-    if (force_grid > 0 && force_grid < max_ctas) max_ctas = force_grid;
-  }
+  if (force_grid > 0 && force_grid < max_ctas) max_ctas = force_grid;
   const int per_cta = (p.num_tiles + max_ctas - 1) / max_ctas;
   {
     // One group in all 512 TMEM columns instead of two alternating halves: the epilogue then no longer overlaps the
     // next group's MMAs, but T doubles (more issuing warps, more weight-tile reuse).  Worth it when a CTA has a
-    // single group anyway, or when half of TMEM holds one tile only.
+    // single group anyway, or when half of TMEM holds fewer than three tiles (n_out >= 96: the weight tiles are
+    // half or more of the bytes a CTA pulls from L2; measured 146 -> 120 us at 155 k rows x 96 channels).
     int t1 = 512 / n_out;
     if (t1 > 8) t1 = 8;
-    if (t1 > T && (per_cta <= t1 || T == 1)) { T = t1; p.nbuf = 1; }
+    if (t1 > T && (per_cta <= t1 || T <= 2)) { T = t1; p.nbuf = 1; }
   }
   if (T > per_cta) T = per_cta;
-  {
-    // developer knob (sweeps of weight-tile re-streaming vs epilogue overlap): SCN_B200_TC_T=<tiles per group>
-    static int force_t = -1;
-    if (force_t < 0) {
-      const char* e = std::getenv("SCN_B200_TC_T");
-      force_t = e ? std::atoi(e) : 0;
-    }
-    if (force_t > 0) {
-      T = force_t;
-      if (T > 8) T = 8;
-      if (T * n_out > 512) T = 512 / n_out;
-      if (T > per_cta) T = per_cta;
-      if (T < 1) T = 1;
-      p.nbuf = T * n_out <= 256 ? 2 : 1;
-    }
+  if (force_t > 0) {
+    T = force_t;
+    if (T > 8) T = 8;
+    if (T * n_out > 512) T = 512 / n_out;
+    if (T > per_cta) T = per_cta;
+    if (T < 1) T = 1;
+    p.nbuf = T * n_out <= 256 ? 2 : 1;
   }
   p.T = T;
-  p.NM = T < tc::MMA_WARPS ? T : tc::MMA_WARPS;
-  p.num_groups = 0;
+  p.NM = T >= 4 ? 4 : (T >= 2 ? 2 : 1);         // classes (issuing warps): a power of two that divides NGRP
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
-  // weight ring: up to 4 tiles (3 in flight behind the one being consumed), within ~72 KB
-  {
-    int sb = (int)((72u * 1024u) / b_bytes);
-    if (sb > tc::MAX_B) sb = tc::MAX_B;
-    if (sb < 2) sb = 2;
-    p.SB = sb;
-  }
   const bool pair = tc_pair(n_in);
   constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 4;
-  const uint32_t fixed = 1024u + (uint32_t)p.SB * b_bytes + 8u * NBAR + 16u + (uint32_t)tc::MAX_A * tc::MASK_BYTES +
-                         (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES * (pair ? 2u : 1u) + 4u * tc::MAX_A + 12u;
-  const uint32_t budget = 226u * 1024u;
-  int SA = (int)((budget - fixed) / tc::A_BYTES);
+  const uint32_t fixed = 1024u + 8u * NBAR + 16u + (uint32_t)tc::MAX_A * tc::MASK_BYTES +
+                         (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES + 16u;
+  const uint32_t budget = 226u * 1024u - fixed;
+  // A ring: a multiple of NGRP slots (every class ring then is a multiple of its producer groups: parity-safe), 8 by
+  // default (measured: depth beyond 6 buys nothing); the weight ring gets the rest, up to MAX_B tiles
+  int SA = 8;
+  if (force_sa > 0) SA = force_sa;
+  SA = SA / tc::NGRP * tc::NGRP;
   if (SA > tc::MAX_A) SA = tc::MAX_A;
-  SA &= ~1;                                      // two A slots per producer warp
-  if (SA < 4) return SCN_ERR_UNSUPPORTED;
+  if (SA < tc::NGRP) SA = tc::NGRP;
+  while (SA > tc::NGRP && (uint32_t)SA * tc::A_BYTES + 2u * b_bytes > budget) SA -= tc::NGRP;
+  if ((uint32_t)SA * tc::A_BYTES + 2u * b_bytes > budget) return SCN_ERR_UNSUPPORTED;
+  int SB = (int)((budget - (uint32_t)SA * tc::A_BYTES) / b_bytes);
+  if (SB > tc::MAX_B) SB = tc::MAX_B;
+  if (force_sb >= 2 && force_sb < SB) SB = force_sb;
   p.SA = SA;
-  size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES;
+  p.SB = SB;
+  const size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES + (size_t)SB * b_bytes;
   int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+  {
+    static bool attr_set = false;          // opt in to > 48 KB of dynamic shared memory, once per kernel
+    if (!attr_set) {
+      SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      SCN_CUDA(cudaFuncSetAttribute(tc::k_conv_tc<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      attr_set = true;
+    }
+  }
   auto launch = [&](auto kern) -> int {
-    SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, tc::THREADS, smem, s>>>(p);
     SCN_LAUNCH_CHECK();
     return SCN_OK;

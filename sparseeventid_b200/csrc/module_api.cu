@@ -9,21 +9,13 @@ extern "C" int scn_conv_module_forward(const void* x, int x_dtype, int64_t n_in_
                                        int64_t n_out_rows, int64_t n_pad, int Cin, int Cout, const float* W,
                                        const float* bias, int precision, void* wimg, int skip_prep, void* out,
                                        int out_dtype, void* stream) {
-  return scn_conv_module_forward_sl(x, x_dtype, n_in_rows, nbr, K, n_out_rows, n_pad, Cin, Cout, W, bias, precision, wimg,
-                                    skip_prep, out, out_dtype, nullptr, stream);
-}
-
-extern "C" int scn_conv_module_forward_sl(const void* x, int x_dtype, int64_t n_in_rows, const int32_t* nbr, int K,
-                                          int64_t n_out_rows, int64_t n_pad, int Cin, int Cout, const float* W,
-                                          const float* bias, int precision, void* wimg, int skip_prep, void* out,
-                                          int out_dtype, const void* stage_lists, void* stream) {
   if (!W || !wimg) return SCN_ERR_ARG;
   if (!skip_prep) {
     int rc = scn_conv_prep_weights(W, K, Cin, Cout, 0, 0, precision, out_dtype, wimg, stream);
     if (rc != SCN_OK) return rc;
   }
-  return scn_conv_forward_sl(x, x_dtype, n_in_rows, nbr, K, n_out_rows, n_pad, Cin, Cout, wimg, bias, precision, out,
-                             out_dtype, stage_lists, stream);
+  return scn_conv_forward(x, x_dtype, n_in_rows, nbr, K, n_out_rows, n_pad, Cin, Cout, wimg, bias, precision, out,
+                          out_dtype, stream);
 }
 
 extern "C" int scn_conv_module_backward(const void* x, int x_dtype, int64_t n_in_rows, const void* dout, int dout_dtype,
@@ -32,18 +24,6 @@ extern "C" int scn_conv_module_backward(const void* x, int x_dtype, int64_t n_in
                                         const float* W, int mirror, int precision, void* wimg_t, int skip_prep,
                                         void* dx, float* dW, int zero_dW, float* dbias, int accumulate_dbias,
                                         double* stats_ws, void* stream) {
-  return scn_conv_module_backward_sl(x, x_dtype, n_in_rows, dout, dout_dtype, n_out_rows, nbr_fwd, n_pad_fwd, nbr_bwd,
-                                     n_pad_bwd, K, Cin, Cout, W, mirror, precision, wimg_t, skip_prep, dx, dW, zero_dW,
-                                     dbias, accumulate_dbias, stats_ws, nullptr, stream);
-}
-
-extern "C" int scn_conv_module_backward_sl(const void* x, int x_dtype, int64_t n_in_rows, const void* dout,
-                                           int dout_dtype, int64_t n_out_rows, const int32_t* nbr_fwd,
-                                           int64_t n_pad_fwd, const int32_t* nbr_bwd, int64_t n_pad_bwd, int K, int Cin,
-                                           int Cout, const float* W, int mirror, int precision, void* wimg_t,
-                                           int skip_prep, void* dx, float* dW, int zero_dW, float* dbias,
-                                           int accumulate_dbias, double* stats_ws, const void* stage_lists_bwd,
-                                           void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (!W || !dout) return SCN_ERR_ARG;
   int rc = SCN_OK;
@@ -53,8 +33,8 @@ extern "C" int scn_conv_module_backward_sl(const void* x, int x_dtype, int64_t n
       rc = scn_conv_prep_weights(W, K, Cin, Cout, 1, mirror, precision, x_dtype, wimg_t, stream);
       if (rc != SCN_OK) return rc;
     }
-    rc = scn_conv_forward_sl(dout, dout_dtype, n_out_rows, nbr_bwd, K, n_in_rows, n_pad_bwd, Cout, Cin, wimg_t, nullptr,
-                             precision, dx, x_dtype, stage_lists_bwd, stream);
+    rc = scn_conv_forward(dout, dout_dtype, n_out_rows, nbr_bwd, K, n_in_rows, n_pad_bwd, Cout, Cin, wimg_t, nullptr,
+                          precision, dx, x_dtype, stream);
     if (rc != SCN_OK) return rc;
   }
   if (dW) {

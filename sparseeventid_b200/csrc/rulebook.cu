@@ -5,7 +5,6 @@
 #include <cub/cub.cuh>
 
 #include "common.cuh"
-#include "stage_lists.cuh"
 
 namespace {
 
@@ -213,99 +212,6 @@ extern "C" int scn_strided_tables(const int32_t* out_row_of_in, const int32_t* o
   if (n_in == 0) return SCN_OK;
   k_strided_tables<<<grid_for(n_in, 256), 256, 0, s>>>(out_row_of_in, off_of_in, n_in, nbr_down, n_out_pad, nbr_up,
                                                        n_in_pad);
-  SCN_LAUNCH_CHECK();
-  return SCN_OK;
-}
-
-// ---- stage lists (stage_lists.cuh): one block per 128-row tile --------------------------------------------------
-namespace {
-constexpr int SL_MAX_K = 128;
-
-__global__ void __launch_bounds__(128) k_stage_lists(const int32_t* __restrict__ nbr, int K, int64_t n_pad, int n_tiles,
-                                                      unsigned char* __restrict__ buf) {
-  __shared__ int s_cnt[SL_MAX_K];
-  __shared__ int s_off[SL_MAX_K];
-  const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* head = reinterpret_cast<uint32_t*>(buf);
-  int2* hdr = reinterpret_cast<int2*>(buf + sl::hdr_offset());
-  uint4* msk = reinterpret_cast<uint4*>(buf + sl::msk_offset(n_tiles, K));
-  int2* ent = reinterpret_cast<int2*>(buf + sl::ent_offset(n_tiles, K));
-  const uint32_t lt = (1u << lane) - 1u;
-  // pass 1: live rows and masks of the tile's K stages
-  for (int k = warp; k < K; k += 4) {
-    const int32_t* src = nbr + (int64_t)k * n_pad + (int64_t)tile * sl::TILE + lane;
-    uint32_t b[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b[i] = __ballot_sync(0xffffffffu, src[32 * i] >= 0);
-    if (lane == 0) {
-      s_cnt[k] = __popc(b[0]) + __popc(b[1]) + __popc(b[2]) + __popc(b[3]);
-      msk[(size_t)tile * K + k] = make_uint4(~b[0], ~b[1], ~b[2], ~b[3]);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int total = 0;
-    for (int k = 0; k < K; ++k) {
-      s_off[k] = total;
-      total += (s_cnt[k] + sl::PAD - 1) & ~(sl::PAD - 1);   // lists are whole passes of the gather loop
-    }
-    const uint32_t base = atomicAdd(head, (uint32_t)total);
-    for (int k = 0; k < K; ++k) {
-      s_off[k] += (int)base;
-      hdr[(size_t)tile * K + k] = make_int2(s_off[k], (s_cnt[k] + sl::PAD - 1) & ~(sl::PAD - 1));
-    }
-  }
-  __syncthreads();
-  // pass 2: the lists (rows ascending within a stage)
-  for (int k = warp; k < K; k += 4) {
-    const int32_t* src = nbr + (int64_t)k * n_pad + (int64_t)tile * sl::TILE + lane;
-    int2* dst = ent + s_off[k];
-    int pos = 0;
-    int2 last = make_int2(0, 0);                        // the stage's last live entry (highest row)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int32_t j = src[32 * i];
-      const uint32_t b = __ballot_sync(0xffffffffu, j >= 0);
-      const int r = 32 * i + lane;
-      const int2 e = make_int2(j, (r << 7) + ((r & 7) << 4));
-      if (j >= 0) dst[pos + __popc(b & lt)] = e;
-      if (b) {
-        const int top = 31 - __clz(b);
-        last = make_int2(__shfl_sync(0xffffffffu, e.x, top), __shfl_sync(0xffffffffu, e.y, top));
-      }
-      pos += __popc(b);
-    }
-    const int padded = (pos + sl::PAD - 1) & ~(sl::PAD - 1);
-    if (pos + lane < padded) dst[pos + lane] = last;    // at most PAD - 1 repeats of the last entry
-  }
-}
-
-__global__ void k_stage_lists_head(unsigned char* buf, int K, int n_tiles) {
-  uint32_t* head = reinterpret_cast<uint32_t*>(buf);
-  head[0] = 0u;
-  head[1] = (uint32_t)K;
-  head[2] = (uint32_t)n_tiles;
-  head[3] = sl::MAGIC;
-}
-}  // namespace
-
-extern "C" size_t scn_stage_lists_bytes(int K, int64_t n_pad) {
-  if (K < 1 || n_pad < 0) return 0;
-  return sl::total_bytes(n_pad / sl::TILE, K);
-}
-
-extern "C" int scn_stage_lists_build(const int32_t* nbr, int K, int64_t n_pad, void* lists, size_t lists_bytes,
-                                     void* stream) {
-  cudaStream_t s = (cudaStream_t)stream;
-  if (K < 1 || K > SL_MAX_K || n_pad < 0 || (n_pad % sl::TILE) != 0 || !lists) return SCN_ERR_ARG;
-  const int64_t n_tiles = n_pad / sl::TILE;
-  if (n_tiles * K * sl::TILE > 0x7fffffffLL) return SCN_ERR_UNSUPPORTED;   // 32-bit entry offsets
-  if (lists_bytes < sl::total_bytes(n_tiles, K)) return SCN_ERR_WORKSPACE;
-  k_stage_lists_head<<<1, 1, 0, s>>>((unsigned char*)lists, K, (int)n_tiles);
-  SCN_LAUNCH_CHECK();
-  if (n_tiles == 0) return SCN_OK;
-  if (!nbr) return SCN_ERR_ARG;
-  k_stage_lists<<<(unsigned)n_tiles, 128, 0, s>>>(nbr, K, n_pad, (int)n_tiles, (unsigned char*)lists);
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }

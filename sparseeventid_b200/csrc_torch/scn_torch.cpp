@@ -57,25 +57,16 @@ void grad_ready(const at::Tensor& p) {
 struct ConvFn : public torch::autograd::Function<ConvFn> {
   static at::Tensor forward(AutogradContext* ctx, at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor nbr_fwd,
                             at::Tensor nbr_bwd, int64_t n_out_rows, bool mirror, int64_t prec, int64_t out_code,
-                            at::Tensor wimg, at::Tensor wimg_t, bool skip_prep, bool direct_w, bool direct_b,
-                            at::Tensor lists) {
-    // lists: stage lists of a submanifold table (nbr_fwd == nbr_bwd), or an empty tensor (the default)
+                            at::Tensor wimg, at::Tensor wimg_t, bool skip_prep, bool direct_w, bool direct_b) {
     x = x.contiguous();
     const int64_t K = weight.size(0), cin = weight.size(-2), cout = weight.size(-1);
     at::Tensor out = at::empty({n_out_rows, cout}, x.options().dtype(out_code == SCN_F32 ? at::kFloat : at::kBFloat16));
-    if (has(lists))
-      check(scn_conv_module_forward_sl(x.data_ptr(), dcode(x), x.size(0), nbr_fwd.data_ptr<int32_t>(), (int)K, n_out_rows,
-                                       nbr_fwd.size(1), (int)cin, (int)cout, weight.data_ptr<float>(),
-                                       has(bias) ? bias.data_ptr<float>() : nullptr, (int)prec, wimg.data_ptr(),
-                                       skip_prep ? 1 : 0, out.data_ptr(), (int)out_code, lists.data_ptr(), cur_stream()),
-            "scn_conv_module_forward_sl");
-    else
     check(scn_conv_module_forward(x.data_ptr(), dcode(x), x.size(0), nbr_fwd.data_ptr<int32_t>(), (int)K, n_out_rows,
                                   nbr_fwd.size(1), (int)cin, (int)cout, weight.data_ptr<float>(),
                                   has(bias) ? bias.data_ptr<float>() : nullptr, (int)prec, wimg.data_ptr(),
                                   skip_prep ? 1 : 0, out.data_ptr(), (int)out_code, cur_stream()),
           "scn_conv_module_forward");
-    ctx->save_for_backward({x, weight, bias, nbr_fwd, nbr_bwd, wimg_t, lists});
+    ctx->save_for_backward({x, weight, bias, nbr_fwd, nbr_bwd, wimg_t});
     ctx->saved_data["n_out_rows"] = n_out_rows;
     ctx->saved_data["mirror"] = mirror;
     ctx->saved_data["prec"] = prec;
@@ -88,7 +79,6 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
   static variable_list backward(AutogradContext* ctx, variable_list grads) {
     auto saved = ctx->get_saved_variables();
     at::Tensor x = saved[0], weight = saved[1], bias = saved[2], nbr_fwd = saved[3], nbr_bwd = saved[4], wimg_t = saved[5];
-    at::Tensor lists = saved[6];
     at::Tensor dout = grads[0].contiguous();
     const int64_t K = weight.size(0), cin = weight.size(-2), cout = weight.size(-1);
     const bool need_dx = ctx->needs_input_grad(0), need_dw = ctx->needs_input_grad(1);
@@ -103,17 +93,6 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
     at::Tensor* btarget = gb.defined() ? &gb : &db;
     double* ws = need_db ? stats_scratch(x.device(), cout).data_ptr<double>() : nullptr;
     TORCH_CHECK(!need_dx || has(wimg_t), "scn_b200: dgrad needs the transposed weight-image workspace");
-    if (has(lists))
-      check(scn_conv_module_backward_sl(x.data_ptr(), dcode(x), x.size(0), dout.data_ptr(), dcode(dout),
-                                        ctx->saved_data["n_out_rows"].toInt(), nbr_fwd.data_ptr<int32_t>(), nbr_fwd.size(1),
-                                        nbr_bwd.data_ptr<int32_t>(), nbr_bwd.size(1), (int)K, (int)cin, (int)cout,
-                                        weight.data_ptr<float>(), ctx->saved_data["mirror"].toBool() ? 1 : 0,
-                                        (int)ctx->saved_data["prec"].toInt(), optr(wimg_t), 0, optr(dx),
-                                        wtarget->defined() ? wtarget->data_ptr<float>() : nullptr, gw.defined() ? 0 : 1,
-                                        btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0, ws,
-                                        lists.data_ptr(), cur_stream()),
-            "scn_conv_module_backward_sl");
-    else
     check(scn_conv_module_backward(x.data_ptr(), dcode(x), x.size(0), dout.data_ptr(), dcode(dout),
                                    ctx->saved_data["n_out_rows"].toInt(), nbr_fwd.data_ptr<int32_t>(), nbr_fwd.size(1),
                                    nbr_bwd.data_ptr<int32_t>(), nbr_bwd.size(1), (int)K, (int)cin, (int)cout,
@@ -126,7 +105,7 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
     if (gw.defined()) grad_ready(weight);
     if (gb.defined()) grad_ready(bias);
     return {dx, dw, db, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(),
-            at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
+            at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor()};
   }
 };
 
@@ -237,14 +216,6 @@ at::Tensor opt(const c10::optional<at::Tensor>& t, const at::Tensor& like) {
   return t.has_value() ? *t : at::empty({0}, like.options().dtype(at::kFloat));
 }
 
-// "no stage lists": one empty tensor per device, reused by every call (never written, so sharing it is safe)
-const at::Tensor& no_lists(const at::Tensor& like) {
-  static std::unordered_map<int, at::Tensor> table;
-  at::Tensor& t = table[like.device().index()];
-  if (!t.defined()) t = at::empty({0}, like.options().dtype(at::kByte));
-  return t;
-}
-
 }  // namespace
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
@@ -253,14 +224,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                    int64_t n_out_rows, bool mirror, int64_t prec, int64_t out_code, at::Tensor wimg,
                    c10::optional<at::Tensor> wimg_t, bool skip_prep, bool direct_w, bool direct_b) {
     return ConvFn::apply(x, weight, opt(bias, x), nbr_fwd, nbr_bwd, n_out_rows, mirror, prec, out_code, wimg, opt(wimg_t, x),
-                         skip_prep, direct_w, direct_b, no_lists(x));
-  });
-  // the same with the stage lists of the (submanifold) table: experimental k_conv_tcl path, SCN_B200_STAGE_LISTS=1
-  m.def("conv_sl", [](at::Tensor x, at::Tensor weight, c10::optional<at::Tensor> bias, at::Tensor nbr_fwd, at::Tensor nbr_bwd,
-                      int64_t n_out_rows, bool mirror, int64_t prec, int64_t out_code, at::Tensor wimg,
-                      c10::optional<at::Tensor> wimg_t, bool skip_prep, bool direct_w, bool direct_b, at::Tensor lists) {
-    return ConvFn::apply(x, weight, opt(bias, x), nbr_fwd, nbr_bwd, n_out_rows, mirror, prec, out_code, wimg, opt(wimg_t, x),
-                         skip_prep, direct_w, direct_b, lists);
+                         skip_prep, direct_w, direct_b);
   });
   m.def("batch_norm", [](at::Tensor x, c10::optional<at::Tensor> weight, c10::optional<at::Tensor> bias, at::Tensor rm,
                          at::Tensor rv, bool training, double eps, double momentum, double leak, bool direct) {

@@ -61,20 +61,6 @@ _side_streams: Dict[torch.device, "torch.cuda.Stream"] = {}
 _side_enabled = os.environ.get("SCN_B200_RULEBOOK_STREAM", "1") not in ("0", "false", "False")
 
 
-_stage_lists = os.environ.get("SCN_B200_STAGE_LISTS", "0") not in ("0", "false", "False", "")
-
-
-def set_stage_lists(flag: bool) -> None:
-    """EXPERIMENTAL (default off, env SCN_B200_STAGE_LISTS=1): submanifold convolutions on the tcgen05 path gather
-    through precomputed per-stage lists (csrc/stage_lists.cuh, csrc/conv_tcl.cu) built once per rulebook."""
-    global _stage_lists
-    _stage_lists = bool(flag)
-
-
-def stage_lists_enabled() -> bool:
-    return _stage_lists
-
-
 def set_rulebook_stream(flag: bool) -> None:
     """Rulebooks on their own CUDA stream (default) or on the caller's stream."""
     global _side_enabled
@@ -139,7 +125,6 @@ class Metadata:
         self.device = torch.device(device)
         self.levels: Dict[Tuple[int, ...], Level] = {}
         self.subm: Dict[tuple, torch.Tensor] = {}
-        self.subm_sl: Dict[tuple, torch.Tensor] = {}   # stage lists of the submanifold tables (experimental, opt-in)
         self.strided: Dict[tuple, StridedRule] = {}
         self.row_of_input = None        # int32 [n_input]
         self.n_input = 0
@@ -205,16 +190,6 @@ class Metadata:
                     ops.subm_rulebook(lvl.keys, lvl.table_keys, lvl.table_vals, lvl.cap, pad3(filt, 1)))
         return self.subm[key]
 
-    def subm_lists(self, spatial, filt) -> torch.Tensor:
-        """Stage lists of subm_table(spatial, filt) (csrc/stage_lists.cuh), built on the rulebook stream on first use."""
-        key = (tuple(spatial), tuple(filt))
-        if key not in self.subm_sl:
-            nbr = self.subm_table(spatial, filt)
-            self.plan.append(("subm_lists", tuple(spatial), tuple(filt)))
-            with self.rulebook_stream() as rs:
-                self.subm_sl[key] = rs.publish(ops.stage_lists(nbr))
-        return self.subm_sl[key]
-
     def strided_rule(self, spatial, filt, stride) -> StridedRule:
         spatial, filt, stride = tuple(spatial), tuple(filt), tuple(stride)
         key = (spatial, filt, stride)
@@ -276,8 +251,6 @@ def prefetch(coords, dimension, spatial_size, plan, ready_event=None):
         try:
             if item[0] == "subm":
                 md.subm_table(item[1], item[2])
-            elif item[0] == "subm_lists":
-                md.subm_lists(item[1], item[2])
             else:
                 md.strided_rule(item[1], item[2], item[3])
         except KeyError:            # a level the plan expects does not exist for this input: leave the rest to the forward

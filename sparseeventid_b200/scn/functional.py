@@ -60,29 +60,15 @@ class ConvFn(Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner=None):
-        return _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, None)
+        return _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner)
 
     @staticmethod
     def backward(ctx, dout):
         return _conv_backward(ctx, dout) + (None,) * 5
 
 
-class ConvSlFn(Function):
-    """ConvFn with the stage lists of a submanifold table (nbr_fwd is nbr_bwd): the experimental k_conv_tcl path
-    (csrc/conv_tcl.cu), used by SubmanifoldConvolution when SCN_B200_STAGE_LISTS=1."""
-
-    @staticmethod
-    def forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists):
-        return _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists)
-
-    @staticmethod
-    def backward(ctx, dout):
-        return _conv_backward(ctx, dout) + (None,) * 6
-
-
-def _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner, lists):
+def _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, owner):
     x = x.contiguous()
-    ctx.lists = lists
     prec = config.precision_code()
     fdt = config.feature_dtype()
     K, cin, cout = weight.shape[0], weight.shape[-2], weight.shape[-1]
@@ -94,14 +80,13 @@ def _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, ow
         if ws.path > 0 and x.dtype != fdt:
             x = ops.convert(x, fdt)
         # always re-laid: fused optimizers update parameters without bumping Tensor._version (see modules._conv)
-        out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False,
-                                      lists=lists)
+        out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False)
         ctx.ws = ws
     else:
         w3 = _w3(weight)
         bprep = ops.prep_weights(w3, False, False, prec, fdt)
         b = bias.detach().float().contiguous() if bias is not None else None
-        out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, fdt, lists=lists)
+        out = ops.conv_forward(x, nbr_fwd, n_out_rows, cin, cout, bprep, b, prec, fdt)
     ctx.save_for_backward(x, weight, bias)
     ctx.nbr_fwd, ctx.nbr_bwd, ctx.mirror, ctx.prec = nbr_fwd, nbr_bwd, mirror, prec
     ctx.n_out_rows = n_out_rows
@@ -135,7 +120,7 @@ def _conv_backward(ctx, dout):
         dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
                                       ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
                                       gw if gw is not None else dw, gw is None,
-                                      gb if gb is not None else db, gb is not None, lists_bwd=ctx.lists)
+                                      gb if gb is not None else db, gb is not None)
         if dx is not None and dx.dtype != x.dtype:
             dx = ops.convert(dx, x.dtype)
         if gw is not None:
@@ -147,7 +132,7 @@ def _conv_backward(ctx, dout):
     if need_dx:
         bt = ops.prep_weights(w3, True, ctx.mirror, ctx.prec, x.dtype)
         dx = ops.conv_forward(dout, ctx.nbr_bwd, x.shape[0], cout, cin, bt, None, ctx.prec, x.dtype,
-                              kind="conv_dgrad", lists=ctx.lists)
+                              kind="conv_dgrad")
     if need_dw:
         dw = ops.conv_wgrad(x, dout, ctx.nbr_fwd, ctx.n_out_rows, cin, cout, ctx.prec).view_as(weight)
         dw = dw.to(weight.dtype)

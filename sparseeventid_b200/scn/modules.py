@@ -121,10 +121,9 @@ class _ConvBase(nn.Module):
             ws = table[key] = F.ConvWorkspace(K, cin, cout, prec, dtype, device)
         return ws
 
-    def _conv(self, x, nbr_fwd, nbr_bwd, n_out_rows, mirror, lists=None):
+    def _conv(self, x, nbr_fwd, nbr_bwd, n_out_rows, mirror):
         """out = bias + conv(x): the C++ autograd function when the torch extension is built (one native call per
-        forward / backward), else functional.ConvFn (same kernels, more interpreter time).  lists: stage lists of a
-        submanifold table (experimental k_conv_tcl path, core.set_stage_lists) or None."""
+        forward / backward), else functional.ConvFn (same kernels, more interpreter time)."""
         ext = _ext.get()
         w, b = self.weight, self.bias
         if (ext is not None and x.is_cuda and not ops.profiling() and w.dtype == torch.float32 and w.is_contiguous()
@@ -140,15 +139,9 @@ class _ConvBase(nn.Module):
             wimg_t = None
             if x.requires_grad and torch.is_grad_enabled():
                 wimg_t = ws.bwd_buffer(K, cin, cout, prec, x.dtype, x.device)
-            if lists is not None:
-                return ext.conv_sl(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, prec, L.SCN_BF16 if fdt == torch.bfloat16
-                                   else L.SCN_F32, ws.fwd, wimg_t, skip, getattr(w, "_scn_direct_grad", False),
-                                   b is not None and getattr(b, "_scn_direct_grad", False), lists)
             return ext.conv(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, prec, L.SCN_BF16 if fdt == torch.bfloat16
                             else L.SCN_F32, ws.fwd, wimg_t, skip, getattr(w, "_scn_direct_grad", False),
                             b is not None and getattr(b, "_scn_direct_grad", False))
-        if lists is not None:
-            return F.ConvSlFn.apply(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, self, lists)
         return F.ConvFn.apply(x, w, b, nbr_fwd, nbr_bwd, n_out_rows, mirror, self)
 
     def _check(self, input):
@@ -174,11 +167,7 @@ class SubmanifoldConvolution(_ConvBase):
         md = input.metadata
         nbr = md.subm_table(input._sp(), self.filter_size)
         n = md.levels[input._sp()].n
-        lists = None
-        if core.stage_lists_enabled() and input.features.is_cuda and self.filter_volume > 1 and ops.conv_path(
-                self.filter_volume, self.nIn, self.nOut, config.precision_code(), config.feature_dtype()) == 2:
-            lists = md.subm_lists(input._sp(), self.filter_size)      # experimental: tcgen05 path only
-        feats = self._conv(input.features, nbr, nbr, n, True, lists)
+        feats = self._conv(input.features, nbr, nbr, n, True)
         return _new_like(input, feats)
 
     def __repr__(self):

@@ -154,20 +154,6 @@ def subm_rulebook(keys, tk, tv, cap, filt) -> torch.Tensor:
     return nbr
 
 
-def stage_lists(nbr) -> torch.Tensor:
-    """Stage lists of a SUBMANIFOLD neighbour table (csrc/stage_lists.cuh): uint8 buffer consumed by the experimental
-    k_conv_tcl convolution (the *_sl entry points).  Built once per rulebook on the current stream."""
-    K, n_pad = nbr.shape
-    nbytes = int(L.lib().scn_stage_lists_bytes(K, n_pad))
-    buf = torch.empty((nbytes,), dtype=torch.uint8, device=nbr.device)
-    p = _profiler
-    e0 = p.begin() if p else None
-    L.check(L.lib().scn_stage_lists_build(L.ptr(nbr), K, n_pad, L.ptr(buf), nbytes, L.stream()), "scn_stage_lists_build")
-    if p:
-        p.end(e0, kind="rulebook_stage_lists", bytes=4.0 * K * n_pad, K=K, rows=n_pad)
-    return buf
-
-
 def strided_rulebook(keys_in, stride):
     """-> (keys_out int64 [n_out] sorted, out_row_of_in int32 [n], off_of_in int32 [n]).  One D2H sync."""
     n = keys_in.shape[0]
@@ -237,8 +223,7 @@ def prep_weights(w3: torch.Tensor, transpose: bool, mirror: bool, prec: int, fea
     return out
 
 
-def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, kind="conv_fwd", lists=None) -> torch.Tensor:
-    """lists: stage lists of `nbr` (submanifold tables only; experimental k_conv_tcl path) or None."""
+def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, kind="conv_fwd") -> torch.Tensor:
     K, n_pad = nbr.shape
     tc = conv_path(K, n_in, n_out, prec, out_dtype) > 0
     if tc and x.dtype != out_dtype:
@@ -246,14 +231,9 @@ def conv_forward(x, nbr, n_out_rows, n_in, n_out, bprep, bias, prec, out_dtype, 
     out = torch.empty((n_out_rows, n_out), dtype=out_dtype, device=x.device)
     p = _profiler
     e0 = p.begin() if p else None
-    if lists is not None:
-        L.check(L.lib().scn_conv_forward_sl(L.ptr(x), L.dtype_code(x), x.shape[0], L.ptr(nbr), K, n_out_rows, n_pad, n_in,
-                                            n_out, L.ptr(bprep), L.ptr(bias), prec, L.ptr(out), L.dtype_code(out),
-                                            L.ptr(lists), L.stream()), "scn_conv_forward_sl")
-    else:
-        L.check(L.lib().scn_conv_forward(L.ptr(x), L.dtype_code(x), x.shape[0], L.ptr(nbr), K, n_out_rows, n_pad, n_in,
-                                         n_out, L.ptr(bprep), L.ptr(bias), prec, L.ptr(out), L.dtype_code(out),
-                                         L.stream()), "scn_conv_forward")
+    L.check(L.lib().scn_conv_forward(L.ptr(x), L.dtype_code(x), x.shape[0], L.ptr(nbr), K, n_out_rows, n_pad, n_in,
+                                     n_out, L.ptr(bprep), L.ptr(bias), prec, L.ptr(out), L.dtype_code(out),
+                                     L.stream()), "scn_conv_forward")
     if p:
         p.end(e0, kind=kind, K=K, n_in=n_in, n_out=n_out, rows_in=x.shape[0], rows_out=n_out_rows, nbr=nbr, tc=tc)
     return out
@@ -278,18 +258,9 @@ def conv_prep_bytes(K, n_in, n_out, prec, feat_dtype) -> int:
     return int(L.lib().scn_conv_prep_bytes(K, n_in, n_out, prec, _DT[feat_dtype]))
 
 
-def conv_module_forward(x, weight, bias, nbr, n_out_rows, K, cin, cout, prec, out_dtype, wimg, skip_prep,
-                        lists=None) -> torch.Tensor:
-    """One C-ABI call: weight re-layout into `wimg` (unless skip_prep) + out = bias + conv(x).  weight/bias fp32.
-    lists: stage lists of `nbr` (submanifold tables only; experimental) or None."""
+def conv_module_forward(x, weight, bias, nbr, n_out_rows, K, cin, cout, prec, out_dtype, wimg, skip_prep) -> torch.Tensor:
+    """One C-ABI call: weight re-layout into `wimg` (unless skip_prep) + out = bias + conv(x).  weight/bias fp32."""
     out = torch.empty((n_out_rows, cout), dtype=out_dtype, device=x.device)
-    if lists is not None:
-        L.check(L.lib().scn_conv_module_forward_sl(x.data_ptr(), _DT[x.dtype], x.shape[0], nbr.data_ptr(), K, n_out_rows,
-                                                   nbr.shape[1], cin, cout, weight.data_ptr(),
-                                                   None if bias is None else bias.data_ptr(), prec, wimg.data_ptr(),
-                                                   int(skip_prep), out.data_ptr(), _DT[out_dtype], lists.data_ptr(),
-                                                   L.stream()), "scn_conv_module_forward_sl")
-        return out
     L.check(L.lib().scn_conv_module_forward(x.data_ptr(), _DT[x.dtype], x.shape[0], nbr.data_ptr(), K, n_out_rows,
                                             nbr.shape[1], cin, cout, weight.data_ptr(),
                                             None if bias is None else bias.data_ptr(), prec, wimg.data_ptr(),
@@ -299,20 +270,10 @@ def conv_module_forward(x, weight, bias, nbr, n_out_rows, K, cin, cout, prec, ou
 
 
 def conv_module_backward(x, dout, weight, nbr_fwd, nbr_bwd, n_out_rows, K, cin, cout, mirror, prec, wimg_t, skip_prep,
-                         need_dx, dw, zero_dw, dbias, accumulate_dbias, lists_bwd=None):
-    """One C-ABI call: dx (returned, or None), dW accumulated into `dw`, dbias (+)= column sums.  Any part may be None.
-    lists_bwd: stage lists of `nbr_bwd` (submanifold tables only; experimental) or None."""
+                         need_dx, dw, zero_dw, dbias, accumulate_dbias):
+    """One C-ABI call: dx (returned, or None), dW accumulated into `dw`, dbias (+)= column sums.  Any part may be None."""
     dx = torch.empty((x.shape[0], cin), dtype=x.dtype, device=x.device) if need_dx else None
     ws = stats_scratch(x.device, cout) if dbias is not None else None
-    if lists_bwd is not None:
-        L.check(L.lib().scn_conv_module_backward_sl(
-            x.data_ptr(), _DT[x.dtype], x.shape[0], dout.data_ptr(), _DT[dout.dtype], n_out_rows,
-            nbr_fwd.data_ptr(), nbr_fwd.shape[1], nbr_bwd.data_ptr(), nbr_bwd.shape[1], K, cin, cout, weight.data_ptr(),
-            int(mirror), prec, None if wimg_t is None else wimg_t.data_ptr(), int(skip_prep),
-            None if dx is None else dx.data_ptr(), None if dw is None else dw.data_ptr(), int(zero_dw),
-            None if dbias is None else dbias.data_ptr(), int(accumulate_dbias), None if ws is None else ws.data_ptr(),
-            lists_bwd.data_ptr(), L.stream()), "scn_conv_module_backward_sl")
-        return dx
     L.check(L.lib().scn_conv_module_backward(
         x.data_ptr(), _DT[x.dtype], x.shape[0], dout.data_ptr(), _DT[dout.dtype], n_out_rows,
         nbr_fwd.data_ptr(), nbr_fwd.shape[1], nbr_bwd.data_ptr(), nbr_bwd.shape[1], K, cin, cout, weight.data_ptr(),

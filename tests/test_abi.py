@@ -48,19 +48,6 @@ def test_header_is_plain_c_and_a_c_caller_links(tmp_path):
     assert "libscn_b200.so" in out and "libtorch" not in out and "libpython" not in out and "libc10" not in out
 
 
-def test_stage_list_layout_arithmetic():
-    """Host-side size function of the (experimental) stage lists against the layout written down in
-    csrc/stage_lists.cuh: 16-byte head, int2 header and uint4 mask per (tile, offset), 128 int2 entries per stage."""
-    from sparseeventid_b200 import _lib, build
-    lib = _lib.load(build.build())
-    for K, n_pad in [(27, 128), (27, 1280), (9, 384), (125, 256), (1, 128), (27, 0)]:
-        n_tiles = n_pad // 128
-        msk_off = 16 + ((n_tiles * K * 8 + 15) & ~15)
-        ent_off = msk_off + n_tiles * K * 16
-        assert lib.scn_stage_lists_bytes(K, n_pad) == ent_off + n_tiles * K * 128 * 8
-    assert lib.scn_stage_lists_bytes(0, 128) == 0
-
-
 def test_library_is_sm100a_only_and_native():
     import subprocess
     from sparseeventid_b200 import build
