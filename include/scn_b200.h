@@ -69,6 +69,13 @@ int64_t scn_hash_capacity(int64_t n);
  * produced by src/io/data_transforms.py:43-46,242) or ncols == dimension (single sample). */
 int scn_pack_coords(const void* coords, int coord_dtype, int64_t n, int ncols, int dimension,
                     uint64_t* keys, void* stream);
+/* The same with a range check: info is int32[4] on the device (zeroed by the caller); info[1] |= 1 when a coordinate
+ * is outside [0, 65535] or a batch index outside [0, 65534] (two sites would alias in the 16-bit key fields; the
+ * host side raises), info[2] = max batch index seen (SCN: batch size = max(argument, max index + 1)).  info[0] and
+ * info[3] are free for the caller (the InputLayer host code has scn_input_layer_rules write n_active to info[0] so
+ * that one read-back returns all three). */
+int scn_pack_coords_checked(const void* coords, int coord_dtype, int64_t n, int ncols, int dimension,
+                            uint64_t* keys, int32_t* info, void* stream);
 /* keys -> int32 [n, 4] rows (x0, x1, x2, batch): SparseConvNetTensor.get_spatial_locations(). */
 int scn_unpack_keys(const uint64_t* keys, int64_t n, int32_t* coords4, void* stream);
 

@@ -12,7 +12,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libscn_b200.so")
+LIB_PATH = os.environ.get("SCN_B200_LIB") or os.path.join(_HERE, "lib", "libscn_b200.so")   # override: debug builds
 
 SCN_F32, SCN_BF16 = 0, 1
 COORD_CODES = {torch.int64: 0, torch.int32: 1, torch.float32: 2, torch.float64: 3}
@@ -26,6 +26,7 @@ SIGNATURES = {
     "scn_launch_count": (C.c_uint64, []),
     "scn_hash_capacity": (_i64, [_i64]),
     "scn_pack_coords": (_i, [_p, _i, _i64, _i, _i, _p, _p]),
+    "scn_pack_coords_checked": (_i, [_p, _i, _i64, _i, _i, _p, _p, _p]),
     "scn_unpack_keys": (_i, [_p, _i64, _p, _p]),
     "scn_hash_build": (_i, [_p, _i64, _p, _p, _i64, _p]),
     "scn_hash_lookup": (_i, [_p, _i64, _p, _p, _i64, _p, _p]),

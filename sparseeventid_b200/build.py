@@ -12,9 +12,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+TAG = os.environ.get("SCN_B200_BUILD_TAG", "")          # e.g. "dbg" with SCN_B200_NVCC_FLAGS=-DSCN_TC_TIMELINE: a second library
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
 LIB_DIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIB_DIR, "libscn_b200.so")
+LIB = os.path.join(LIB_DIR, "libscn_b200" + ("_" + TAG if TAG else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Wno-deprecated-declarations",

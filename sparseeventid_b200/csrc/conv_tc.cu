@@ -85,6 +85,8 @@ struct Params {
   int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
   int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
   unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
+  int exp;                      // -DSCN_TC_TIMELINE builds only: timing experiments with WRONG results (SCN_B200_TC_EXP):
+                                // 1 no gather copies, 2 no MMAs, 4 no output stores
 };
 
 // NCH: 64-channel chunks per offset = ceil(n_in / 64).  PAIR (n_in == 32, NCH == 1): one stage holds TWO offsets,
@@ -115,8 +117,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   // warp index through a broadcast shuffle: the compiler then knows it is warp-uniform (role branches, barrier
   // addresses and slot numbers stay in uniform registers instead of per-lane copies with R2UR waterfalls)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  // timeline marks: dbg[((role * 256 + stage) * 8 + event)] = clock64(), CTA 0 only, first 256 stages
-  // (compiled in only with -DSCN_TC_TIMELINE: the marks cost the single-warp issue loops real time)
+  // timeline marks: dbg[((role * 256 + stage) * 8 + event)] = clock64(), CTA 0 only, first 256 stages of each role
+  // (compiled in only with -DSCN_TC_TIMELINE: the marks cost the single-warp issue loops real time).  Roles: 0-3
+  // producer groups, 4-7 issuing warps (per stage), 8 weight loader, 9 epilogue warp 0, 10-13 issuing warps (per q)
   auto mark = [&](int role, int stage, int ev) {
 #ifdef SCN_TC_TIMELINE
     if (p.dbg != nullptr && blockIdx.x == 0 && lane == 0 && stage < 256)
@@ -125,6 +128,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     (void)role; (void)stage; (void)ev;
 #endif
   };
+#ifdef SCN_TC_TIMELINE
+  const int exp_flags = p.exp;
+#else
+  constexpr int exp_flags = 0;
+#endif
 
   if (warp == WARP_MMA) {
     if (lane == 0) {
@@ -208,24 +216,37 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     auto valid = [&]() { return g < my_groups && cls < tv; };
     for (int i = 0; i < sub; ++i)
       if (valid()) step();
-    // neighbour index of this lane's row for a stage (PAIR: of both offsets)
-    auto load_idx = [&](int& jl, int& jh) {
-      const int stp = PAIR ? q : q / NCH;
-      const int64_t tile = (int64_t)tile_lo + (int64_t)g * T + t;
-      const int k0 = PAIR ? 2 * stp : stp;
-      const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + myrow;
-      jl = ldg_nc32(src);
-      jh = (PAIR && (k0 + 1 < p.K)) ? ldg_nc32(src + p.n_pad) : -1;
+    // Neighbour indices are fetched TWO stages ahead (the cursor runs ahead of the stage being gathered): one stage of
+    // lead (~500 cycles of this warp's own work) does not cover an L2 round trip under load, and the stall at the
+    // ballot below was ~400 of the ~1300 cycles a stage cost its producer warp (profiles/r02b_tc_timeline.txt).
+    // A fetch returns the stage's q (-1: no stage left), so the cursor never has to be rewound.
+    auto fetch = [&](int& jl_, int& jh_, int& q_) {
+      q_ = -1; jl_ = -1; jh_ = -1;
+      if (valid()) {
+        const int stp = PAIR ? q : q / NCH;
+        const int64_t tile = (int64_t)tile_lo + (int64_t)g * T + t;
+        const int k0 = PAIR ? 2 * stp : stp;
+        const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + myrow;
+        jl_ = ldg_nc32(src);
+        if (PAIR && (k0 + 1 < p.K)) jh_ = ldg_nc32(src + p.n_pad);
+        q_ = q;
+        for (int i = 0; i < gpc; ++i) step();
+      }
     };
 
-    int jl = -1, jh = -1;
-    if (valid()) load_idx(jl, jh);
+    int jl, jh, qc, jl1, jh1, q1;
+    fetch(jl, jh, qc);
+    fetch(jl1, jh1, q1);
     int ls = sub;                                        // slot within the class ring (sub < gpc <= spc)
     uint32_t round = 0;
-    while (valid()) {
+    int it = 0;
+    while (qc >= 0) {
+      if (wq == 0) mark(grp, it, 0);
+      int jl2, jh2, q2;
+      fetch(jl2, jh2, q2);                               // two stages ahead
       const int slot = cls * spc + ls;
-      const int cc = PAIR ? 0 : q % NCH;
-      const bool full = (q == 0);                        // first stage of a tile: unmasked MMA, every row written
+      const int cc = PAIR ? 0 : qc % NCH;
+      const bool full = (qc == 0);                       // first stage of a tile: unmasked MMA, every row written
       const uint32_t dst = drow + (uint32_t)slot * A_BYTES;
       // ---- live rows -> list (full stage: every row, missing ones as zeros) ----------------------------------
       const uint32_t bl = __ballot_sync(0xffffffffu, jl >= 0);
@@ -244,12 +265,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         }
       }
       __syncwarp();
-      // prefetch the next stage's indices (consumed in the next iteration)
-      for (int i = 0; i < gpc; ++i) step();
-      if (valid()) load_idx(jl, jh);
+      if (wq == 0) mark(grp, it, 1);
 
       // the MMAs that read this slot's previous stage have retired
       mbar_wait(aempty(slot), (round & 1u) ^ 1u);
+      if (wq == 0) mark(grp, it, 2);
       if (lane == 0) {
         amask[slot * 8 + wq] = ~bl;
         if (PAIR) amask[slot * 8 + 4 + wq] = ~bh;
@@ -257,7 +277,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       const int npass = (nlive + IPP - 1) / IPP;         // <= 8
       const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
       const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
-      if (lane_on) {
+      if (lane_on && !(exp_flags & 1)) {
         if (!full) {
           // hot path per pass: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
           for (int p0 = 0; p0 < npass; p0 += 4) {        // 4 list entries are read before their copies are issued
@@ -287,8 +307,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       cp_async_arrive_noinc(afull(slot));
       if (lane == 0) mbar_arrive(afull(slot));
       __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
+      if (wq == 0) mark(grp, it, 3);
+      ++it;
       ls += gpc;
       if (ls >= spc) { ls -= spc; ++round; }
+      jl = jl1; jh = jh1; qc = q1;
+      jl1 = jl2; jh1 = jh2; q1 = q2;
     }
   } else if (warp == WARP_BLOAD) {
     // ================================ weight-tile loader (1 elected lane, bulk async copies) ==
@@ -298,9 +322,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     int bslot = 0;
     uint32_t bround = 0;
     for (int i = 0; i < total_b; ++i) {
-      mark(2, i, 0);
+      mark(8, i, 0);
       mbar_wait(bempty(bslot), (bround & 1u) ^ 1u);
-      mark(2, i, 1);
+      mark(8, i, 1);
       if (elect_one()) {
         mbar_expect_tx(bfull(bslot), b_bytes);
         bulk_g2s(b_base + (uint32_t)bslot * b_bytes, p.bimg + (size_t)(i % Q) * b_bytes, b_bytes, bfull(bslot));
@@ -322,6 +346,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       uint32_t bround = 0;
       int ls = 0;                                                     // this class's next stage: slot m * spc + ls ...
       uint32_t around = 0;                                            // ... in round `around` of that slot
+      int it = 0;
       for (int g = 0; g < my_groups; ++g) {
         const int buf = nbuf == 2 ? (g & 1) : 0;
         const uint32_t use = (uint32_t)(nbuf == 2 ? (g >> 1) : g);    // how many times this buffer has been used before
@@ -331,15 +356,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         for (int q = 0; q < Q; ++q) {
           const int cc = PAIR ? 0 : q % NCH;
           const int step = PAIR ? q : q / NCH;
-          mark(3, g * Q + q, 0);
+          mark(10 + m, g * Q + q, 0);
           mbar_wait(bfull(bslot), bround & 1u);
-          mark(3, g * Q + q, 1);
+          mark(10 + m, g * Q + q, 1);
           const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
           // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
           const int nk = PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4);
           for (int t = m; t < tv; t += NM) {
             const int aslot = m * spc + ls;
+            mark(4 + m, it, 0);
             mbar_wait(afull(aslot), around & 1u);            // all four quarters of the stage have landed (and their masks)
+            mark(4 + m, it, 1);
             tc_fence_after();
             // disable-output-lane masks published by the stage's producers: bit r set <=> output row r has no
             // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
@@ -364,7 +391,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
             if (elect_one()) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
-                if (kk < nk) {
+                if (kk < nk && !(exp_flags & 2)) {
                   const bool hi = PAIR && kk >= 2;
                   umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
                               hi ? h0 : m0, hi ? h1 : m1, hi ? h2 : m2, hi ? h3 : m3);
@@ -373,6 +400,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
               umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
             }
             __syncwarp();
+            mark(4 + m, it, 2);
+            ++it;
             if (++ls == spc) { ls = 0; ++around; }
           }
           if (elect_one()) umma_commit(bempty(bslot));
@@ -387,7 +416,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     // ================================ epilogue (warps 0..3) ==================================
     for (int g = 0; g < my_groups; ++g) {
       const int buf = p.nbuf == 2 ? (g & 1) : 0;
+      if (warp == 0) mark(9, g, 0);
       mbar_wait_sleep(accf(buf), (uint32_t)(p.nbuf == 2 ? (g >> 1) : g) & 1u);
+      if (warp == 0) mark(9, g, 1);
       tc_fence_after();
       const int tv = tiles_in_group(g);
       for (int t = 0; t < tv; ++t) {
@@ -397,7 +428,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         for (int c0 = 0; c0 < p.n_out; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + (uint32_t)c0, v);
-          if (row < p.n_rows) {
+          if (row < p.n_rows && !(exp_flags & 4)) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.n_out + c0);
 #pragma unroll
             for (int gq = 0; gq < 4; ++gq) {
@@ -415,6 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 0) mark(9, g, 2);
       if (lane == 0) mbar_arrive(acce(buf));
     }
   }
@@ -453,6 +485,13 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
 // Debug: device buffer of 4 roles x 256 stages x 8 marks (uint64) filled by CTA 0 of the following launches; NULL disables.
 static unsigned long long* g_tc_dbg = nullptr;
 extern "C" void scn_tc_debug_timeline(void* device_buffer) { g_tc_dbg = (unsigned long long*)device_buffer; }
+// timing experiments (WRONG results; honoured only by -DSCN_TC_TIMELINE builds): 1 no gather copies, 2 no MMAs, 4 no stores
+#ifdef SCN_TC_TIMELINE
+static int g_tc_exp = 0;
+extern "C" void scn_tc_debug_exp(int flags) { g_tc_exp = flags; }
+#else
+extern "C" void scn_tc_debug_exp(int) {}
+#endif
 
 bool scn_tc_disabled() {
   static int v = -1;
@@ -509,6 +548,11 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   const int force_grid = g_knob[0], force_t = g_knob[1], force_sa = g_knob[2], force_sb = g_knob[3];
   tc::Params p;
   p.dbg = g_tc_dbg;
+#ifdef SCN_TC_TIMELINE
+  p.exp = g_tc_exp;
+#else
+  p.exp = 0;
+#endif
   p.in = in; p.nbr = nbr; p.bimg = (const unsigned char*)bimg; p.bias = bias; p.out = out;
   p.n_rows = n_rows; p.n_pad = n_pad; p.K = K; p.n_in = n_in; p.n_out = n_out;
   const int nch = (n_in + tc::KC - 1) / tc::KC;

@@ -652,20 +652,20 @@ __global__ void k_pool_rows(const T* __restrict__ x, int ldx, const int32_t* __r
 }
 
 template <typename T>
-__global__ void k_s2d_fwd(const T* __restrict__ x, const uint64_t* __restrict__ keys, int64_t n, int C, int s0, int s1,
-                          int s2, float* __restrict__ dense) {
+__global__ void k_s2d_fwd(const T* __restrict__ x, const uint64_t* __restrict__ keys, int64_t n, int C, int batch, int s0,
+                          int s1, int s2, float* __restrict__ dense) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * C) return;
   int64_t r = i / C;
   int c = (int)(i - r * C);
   int x0, x1, x2, b;
   key_unpack(keys[r], x0, x1, x2, b);
-  if (x0 >= s0 || x1 >= s1 || x2 >= s2) return;
+  if (x0 >= s0 || x1 >= s1 || x2 >= s2 || b >= batch) return;      // a site outside the dense volume is dropped, never written
   dense[((((int64_t)b * C + c) * s0 + x0) * s1 + x1) * s2 + x2] = Elem<T>::ld(x + i);
 }
 template <typename T>
-__global__ void k_s2d_bwd(const float* __restrict__ ddense, const uint64_t* __restrict__ keys, int64_t n, int C, int s0,
-                          int s1, int s2, T* __restrict__ dx) {
+__global__ void k_s2d_bwd(const float* __restrict__ ddense, const uint64_t* __restrict__ keys, int64_t n, int C, int batch,
+                          int s0, int s1, int s2, T* __restrict__ dx) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n * C) return;
   int64_t r = i / C;
@@ -673,7 +673,7 @@ __global__ void k_s2d_bwd(const float* __restrict__ ddense, const uint64_t* __re
   int x0, x1, x2, b;
   key_unpack(keys[r], x0, x1, x2, b);
   float v = 0.f;
-  if (x0 < s0 && x1 < s1 && x2 < s2) v = ddense[((((int64_t)b * C + c) * s0 + x0) * s1 + x1) * s2 + x2];
+  if (x0 < s0 && x1 < s1 && x2 < s2 && b < batch) v = ddense[((((int64_t)b * C + c) * s0 + x0) * s1 + x1) * s2 + x2];
   Elem<T>::st(dx + i, v);
 }
 
@@ -1022,8 +1022,8 @@ extern "C" int scn_sparse_to_dense_forward(const void* x, int dtype, const uint6
   SCN_CUDA(cudaMemsetAsync(dense, 0, total * sizeof(float), s));
   if (n == 0) return SCN_OK;
   unsigned g = grid_for(n * C, 256);
-  if (dtype == SCN_F32) k_s2d_fwd<float><<<g, 256, 0, s>>>((const float*)x, keys, n, C, s0, s1, s2, dense);
-  else if (dtype == SCN_BF16) k_s2d_fwd<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, keys, n, C, s0, s1, s2, dense);
+  if (dtype == SCN_F32) k_s2d_fwd<float><<<g, 256, 0, s>>>((const float*)x, keys, n, C, batch, s0, s1, s2, dense);
+  else if (dtype == SCN_BF16) k_s2d_fwd<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)x, keys, n, C, batch, s0, s1, s2, dense);
   else return SCN_ERR_ARG;
   SCN_LAUNCH_CHECK();
   return SCN_OK;
@@ -1032,11 +1032,10 @@ extern "C" int scn_sparse_to_dense_forward(const void* x, int dtype, const uint6
 extern "C" int scn_sparse_to_dense_backward(const float* ddense, const uint64_t* keys, int64_t n, int C, int batch,
                                             int s0, int s1, int s2, void* dx, int dtype, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  (void)batch;
   if (n == 0) return SCN_OK;
   unsigned g = grid_for(n * C, 256);
-  if (dtype == SCN_F32) k_s2d_bwd<float><<<g, 256, 0, s>>>(ddense, keys, n, C, s0, s1, s2, (float*)dx);
-  else if (dtype == SCN_BF16) k_s2d_bwd<__nv_bfloat16><<<g, 256, 0, s>>>(ddense, keys, n, C, s0, s1, s2, (__nv_bfloat16*)dx);
+  if (dtype == SCN_F32) k_s2d_bwd<float><<<g, 256, 0, s>>>(ddense, keys, n, C, batch, s0, s1, s2, (float*)dx);
+  else if (dtype == SCN_BF16) k_s2d_bwd<__nv_bfloat16><<<g, 256, 0, s>>>(ddense, keys, n, C, batch, s0, s1, s2, (__nv_bfloat16*)dx);
   else return SCN_ERR_ARG;
   SCN_LAUNCH_CHECK();
   return SCN_OK;

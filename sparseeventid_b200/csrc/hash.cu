@@ -7,15 +7,35 @@
 
 namespace {
 
+// info (optional, int32[4]): [1] |= 1 when a coordinate or batch index does not fit its 16-bit key field (negative, or
+// >= 65536 / batch >= 65535: the packed keys of two different sites would alias), [2] = max batch index seen.
 template <typename T>
-__global__ void k_pack_coords(const T* __restrict__ c, int64_t n, int ncols, int dim, uint64_t* __restrict__ keys) {
+__global__ void k_pack_coords(const T* __restrict__ c, int64_t n, int ncols, int dim, uint64_t* __restrict__ keys,
+                              int32_t* __restrict__ info) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const T* r = c + i * ncols;
-  int x[3] = {0, 0, 0};
-  for (int a = 0; a < dim && a < 3; ++a) x[a] = (int)(long long)r[a];
-  int b = ncols > dim ? (int)(long long)r[dim] : 0;
-  keys[i] = key_pack(x[0], x[1], x[2], b);
+  int b = 0;
+  bool bad = false;
+  if (i < n) {
+    const T* r = c + i * ncols;
+    int x[3] = {0, 0, 0};
+    for (int a = 0; a < dim && a < 3; ++a) {
+      const long long v = (long long)r[a];
+      bad |= v < 0 || v > 65535;
+      x[a] = (int)v;
+    }
+    const long long bv = ncols > dim ? (long long)r[dim] : 0;
+    bad |= bv < 0 || bv >= 65535;
+    b = (int)bv;
+    keys[i] = key_pack(x[0], x[1], x[2], b);
+  }
+  if (info != nullptr) {
+    const int bmax = __reduce_max_sync(0xffffffffu, bad ? 0 : b);
+    const bool any_bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (any_bad) atomicOr(info + 1, 1);
+      if (bmax > 0) atomicMax(info + 2, bmax);
+    }
+  }
 }
 
 __global__ void k_unpack_keys(const uint64_t* __restrict__ keys, int64_t n, int4* __restrict__ out) {
@@ -128,22 +148,27 @@ extern "C" int64_t scn_hash_capacity(int64_t n) {
   return c;
 }
 
-extern "C" int scn_pack_coords(const void* coords, int coord_dtype, int64_t n, int ncols, int dimension,
-                               uint64_t* keys, void* stream) {
+extern "C" int scn_pack_coords_checked(const void* coords, int coord_dtype, int64_t n, int ncols, int dimension,
+                                       uint64_t* keys, int32_t* info, void* stream) {
   if (n == 0) return SCN_OK;
   if (!coords || !keys || dimension < 1 || dimension > 3 || (ncols != dimension && ncols != dimension + 1))
     return SCN_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   unsigned g = grid_for(n, 256);
   switch (coord_dtype) {
-    case SCN_COORD_I64: k_pack_coords<long long><<<g, 256, 0, s>>>((const long long*)coords, n, ncols, dimension, keys); break;
-    case SCN_COORD_I32: k_pack_coords<int><<<g, 256, 0, s>>>((const int*)coords, n, ncols, dimension, keys); break;
-    case SCN_COORD_F32: k_pack_coords<float><<<g, 256, 0, s>>>((const float*)coords, n, ncols, dimension, keys); break;
-    case SCN_COORD_F64: k_pack_coords<double><<<g, 256, 0, s>>>((const double*)coords, n, ncols, dimension, keys); break;
+    case SCN_COORD_I64: k_pack_coords<long long><<<g, 256, 0, s>>>((const long long*)coords, n, ncols, dimension, keys, info); break;
+    case SCN_COORD_I32: k_pack_coords<int><<<g, 256, 0, s>>>((const int*)coords, n, ncols, dimension, keys, info); break;
+    case SCN_COORD_F32: k_pack_coords<float><<<g, 256, 0, s>>>((const float*)coords, n, ncols, dimension, keys, info); break;
+    case SCN_COORD_F64: k_pack_coords<double><<<g, 256, 0, s>>>((const double*)coords, n, ncols, dimension, keys, info); break;
     default: return SCN_ERR_ARG;
   }
   SCN_LAUNCH_CHECK();
   return SCN_OK;
+}
+
+extern "C" int scn_pack_coords(const void* coords, int coord_dtype, int64_t n, int ncols, int dimension,
+                               uint64_t* keys, void* stream) {
+  return scn_pack_coords_checked(coords, coord_dtype, n, ncols, dimension, keys, nullptr, stream);
 }
 
 extern "C" int scn_unpack_keys(const uint64_t* keys, int64_t n, int32_t* coords4, void* stream) {

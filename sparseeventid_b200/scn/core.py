@@ -127,6 +127,7 @@ class Metadata:
         self.subm: Dict[tuple, torch.Tensor] = {}
         self.strided: Dict[tuple, StridedRule] = {}
         self.row_of_input = None        # int32 [n_input]
+        self.max_batch_index = -1       # largest batch index among the input rows (read back with n_active)
         self.n_input = 0
         self.batch_size = 0
         self.input_spatial = None
@@ -138,10 +139,15 @@ class Metadata:
         """InputLayer rules: packed keys, first-appearance row numbering, hash table of the input level."""
         spatial = tuple(spatial)
         with self.rulebook_stream(join_first=True) as rs:
-            keys = ops.pack_coords(coords, self.dimension)
-            rows, keys_out, tk, tv, cap = ops.input_layer_rules(keys)
+            info = torch.zeros((4,), dtype=torch.int32, device=coords.device)
+            keys = ops.pack_coords(coords, self.dimension, info)
+            rows, keys_out, tk, tv, cap, got = ops.input_layer_rules(keys, info)
             lvl = self.add_level(spatial, keys_out, (tk, tv, cap))
             rs.publish(rows, keys_out, tk, tv)
+        if got[1]:
+            raise ValueError("InputLayer: coordinates must lie in [0, 65535] and batch indices in [0, 65534] "
+                             "(16-bit fields of the packed site keys); got values outside that range")
+        self.max_batch_index = int(got[2]) if keys.shape[0] else -1
         self.row_of_input = rows
         self.n_input = int(keys.shape[0])
         self.input_spatial = spatial

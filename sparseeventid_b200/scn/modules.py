@@ -72,10 +72,8 @@ class InputLayer(nn.Module):
         rows = md.row_of_input
         keys_out = lvl.keys
         self._last_plan = md.plan                                    # filled as the network asks for rulebooks
-        if batch_size > 0 or lvl.n == 0:
-            md.batch_size = batch_size            # given by the caller (the reference always passes it): no device sync
-        else:
-            md.batch_size = int((keys_out.max() >> 48).item()) + 1
+        # SCN: batch size = max(argument, largest batch index + 1); the index came back with the row count (no extra sync)
+        md.batch_size = max(batch_size, md.max_batch_index + 1)
         out = SparseConvNetTensor(None, md, self.spatial_size)
         out.features = F.InputLayerFn.apply(feats, rows, lvl.n, self.mode)
         return out

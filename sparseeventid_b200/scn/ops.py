@@ -79,15 +79,17 @@ def pad128(n: int) -> int:
 # ---------------------------------------------------------------------------- hash / rulebooks
 
 
-def pack_coords(coords: torch.Tensor, dimension: int) -> torch.Tensor:
+def pack_coords(coords: torch.Tensor, dimension: int, info: torch.Tensor = None) -> torch.Tensor:
+    """info: optional zeroed int32[4] device tensor; [1] is set when a coordinate / batch index does not fit its 16-bit
+    key field, [2] receives the largest batch index (see scn_pack_coords_checked)."""
     L.require_cuda(coords, "pack_coords")
     if coords.dtype not in L.COORD_CODES:
         coords = coords.long()
     coords = coords.contiguous()
     n, ncols = coords.shape
     keys = torch.empty((n,), dtype=torch.int64, device=coords.device)
-    L.check(L.lib().scn_pack_coords(L.ptr(coords), L.COORD_CODES[coords.dtype], n, ncols, dimension, L.ptr(keys),
-                                    L.stream()), "scn_pack_coords")
+    L.check(L.lib().scn_pack_coords_checked(L.ptr(coords), L.COORD_CODES[coords.dtype], n, ncols, dimension, L.ptr(keys),
+                                            L.ptr(info), L.stream()), "scn_pack_coords")
     return keys
 
 
@@ -120,14 +122,15 @@ def hash_lookup(queries: torch.Tensor, tk, tv, cap) -> torch.Tensor:
     return out
 
 
-def input_layer_rules(keys_in: torch.Tensor):
-    """-> (row_of_input int32 [n], keys_out int64 [n_active], table_keys, table_vals, cap).  One D2H sync."""
+def input_layer_rules(keys_in: torch.Tensor, info: torch.Tensor = None):
+    """-> (row_of_input int32 [n], keys_out int64 [n_active], table_keys, table_vals, cap, info list).  One D2H sync:
+    `info` (the int32[4] tensor pack_coords filled) comes back as [n_active, range violation flag, max batch index, 0]."""
     n = keys_in.shape[0]
     dev = keys_in.device
     tk, tv, cap = new_table(n, dev)
     rows = _i32(n, dev)
     keys_out = torch.empty((n,), dtype=torch.int64, device=dev)
-    n_active = torch.zeros((1,), dtype=torch.int32, device=dev)
+    n_active = info if info is not None else torch.zeros((4,), dtype=torch.int32, device=dev)
     ws_bytes = int(L.lib().scn_input_rules_workspace(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     p = _profiler
@@ -136,8 +139,9 @@ def input_layer_rules(keys_in: torch.Tensor):
                                           L.ptr(n_active), L.ptr(ws), ws_bytes, L.stream()), "scn_input_layer_rules")
     if p:
         p.end(e0, kind="rulebook_input", bytes=20.0 * n, rows=n)
-    na = int(n_active.item())
-    return rows, keys_out[:na], tk, tv, cap
+    got = n_active.tolist()
+    na = int(got[0])
+    return rows, keys_out[:na], tk, tv, cap, got
 
 
 def subm_rulebook(keys, tk, tv, cap, filt) -> torch.Tensor:

@@ -5,7 +5,10 @@ mkdir -p gpurun_out
 step() { echo; echo "=== $1"; shift; "$@"; local rc=$?; echo "--- rc=$rc"; return $rc; }
 for s in "$@"; do
   case "$s" in
-    tests) step "gpu suite" timeout 500 python -m pytest tests -m gpu -x -q || exit 1 ;;
+    tests) step "gpu suite" timeout 700 python -m pytest tests -m gpu -x -q || exit 1 ;;
+    tests_nf) step "gpu suite (non-fatal)" timeout 700 python -m pytest tests -m gpu -q ;;
+    timeline2) for a in "495518 27 32 32" "317485 27 64 64"; do step "timeline $a" env SCN_B200_LIB=sparseeventid_b200/lib/libscn_b200_dbg.so timeout 120 python tools/tc_timeline.py $a; done ;;
+    timeline) for a in "495518 27 32 32" "317485 27 64 64" "317485 27 64 64 1" "154605 27 96 96" "7332 27 192 192"; do step "timeline $a" env SCN_B200_LIB=sparseeventid_b200/lib/libscn_b200_dbg.so timeout 120 python tools/tc_timeline.py $a; done ;;
     convtests) step "conv kernel tests" timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q || exit 1 ;;
     smoke) step "smoke" timeout 120 python -c "import __graft_entry__ as g; g.smoke()" || exit 1 ;;
     sweep) for i in 0 1 2 3 4 5; do step "tc sweep shape $i" timeout 200 python tools/tc_sweep.py full $i; done ;;
