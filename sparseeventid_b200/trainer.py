@@ -52,6 +52,7 @@ class FlatGradArena:
                 b_start, b_count = off, 0
         if b_count:
             self.buckets.append((b_start, off, b_count))
+        self._views = [p.grad for p in self.params]
         self._pending = [0] * len(self.buckets)
         self._works = []
         self._hooks = []
@@ -74,7 +75,16 @@ class FlatGradArena:
             if ext is not None:      # the C++ autograd functions report completed in-place gradients through this
                 ext.set_grad_ready_callback(lambda t: self._on_grad(self._param_of_ptr[t.data_ptr()]))
 
+    def _bind(self):
+        """(Re-)points every parameter's .grad at its slice of the arena.  optimizer.zero_grad() / model.zero_grad()
+        default to set_to_none=True: autograd would then allocate fresh gradient tensors, the kernels' in-place
+        accumulation would fall back, and finish() would all-reduce a stale buffer (ranks silently diverge)."""
+        for p, view in zip(self.params, self._views):        # identity test: ~50 ns per parameter
+            if p.grad is not view:
+                p.grad = view
+
     def zero(self):
+        self._bind()
         self.flat.zero_()
         self._pending = [c for (_, _, c) in self.buckets]
         self._works = []
@@ -90,6 +100,10 @@ class FlatGradArena:
         """Waits for the in-flight bucket all-reduces and turns the sums into means."""
         if self.world == 1:
             return
+        for p, view in zip(self.params, self._views):        # a gradient that left the arena would never be averaged
+            if p.grad is not view:
+                raise RuntimeError("FlatGradArena: a parameter's .grad no longer points into the arena (zero_grad with "
+                                   "set_to_none=True after arena.zero()?); call arena.zero() at the start of every step")
         if not self.overlap:
             if dist.get_backend(self.group) == "nccl":
                 dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group)
@@ -123,9 +137,17 @@ def warmup_flat_lr(step: int, peak: float = 3e-3, warmup_steps: int = 100) -> fl
 # ------------------------------------------------------------------------------------------------
 
 
-def checkpoint_dict(model: torch.nn.Module, optimizer=None, scheduler=None, global_step: int = 0) -> dict:
-    """The subset of a Lightning checkpoint the reference reads back (+ optimizer / scheduler state, Lightning names)."""
-    ck = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "global_step": int(global_step)}
+LIGHTNING_VERSION = "2.0.0"      # the envelope below is the one pytorch_lightning 2.x writes and validates on resume
+
+
+def checkpoint_dict(model: torch.nn.Module, optimizer=None, scheduler=None, global_step: int = 0, epoch: int = 0) -> dict:
+    """A checkpoint the reference can resume from: `pl.Trainer.fit(ckpt_path=...)` (create_trainer.py:107-115) reads
+    "state_dict", "optimizer_states", "lr_schedulers", "epoch", "global_step", "pytorch-lightning_version", "loops" and
+    "callbacks"; the last three are written as the minimal envelope Lightning accepts (loop progress restarts from the
+    recorded global step, callback state empty)."""
+    ck = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()}, "global_step": int(global_step),
+          "epoch": int(epoch), "pytorch-lightning_version": LIGHTNING_VERSION, "loops": {}, "callbacks": {},
+          "optimizer_states": [], "lr_schedulers": []}
     if optimizer is not None:
         ck["optimizer_states"] = [optimizer.state_dict()]
     if scheduler is not None:
@@ -136,7 +158,10 @@ def checkpoint_dict(model: torch.nn.Module, optimizer=None, scheduler=None, glob
 def restore_checkpoint(model: torch.nn.Module, checkpoint: dict, encoder_only: bool = False, optimizer=None,
                        scheduler=None) -> int:
     """Loads a Lightning-layout checkpoint (this repo's or the reference's) into `model`; returns its global step.
-    encoder_only mirrors create_trainer.py:94-106: only the encoder's tensors are loaded and the encoder is frozen."""
+    encoder_only mirrors create_trainer.py:94-106: only the encoder's tensors are loaded and the encoder is frozen.
+    A reference checkpoint may carry tensors of the LightningModule that are not part of the networks (e.g.
+    `criterion.weight` with loss_balance_scheme=even, supervised_eventID.py): keys outside `encoder.` / `head.` are
+    ignored; a key the model needs and the checkpoint lacks is an error."""
     sd = checkpoint["state_dict"]
     if encoder_only:
         enc = {k.replace("encoder.", ""): v for k, v in sd.items() if "encoder" in k}
@@ -144,7 +169,10 @@ def restore_checkpoint(model: torch.nn.Module, checkpoint: dict, encoder_only: b
         for p in model.encoder.parameters():
             p.requires_grad = False
         return int(checkpoint.get("global_step", 0))
-    model.load_state_dict(sd)
+    own = {k: v for k, v in sd.items() if k.startswith("encoder.") or k.startswith("head.")}
+    missing, unexpected = model.load_state_dict(own, strict=False)
+    if missing or unexpected:
+        raise KeyError(f"checkpoint does not match the model: missing {list(missing)[:5]}, unexpected {list(unexpected)[:5]}")
     if optimizer is not None and checkpoint.get("optimizer_states"):
         optimizer.load_state_dict(checkpoint["optimizer_states"][0])
     if scheduler is not None and checkpoint.get("lr_schedulers"):

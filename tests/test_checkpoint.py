@@ -54,3 +54,27 @@ def test_restore_encoder_only_freezes_the_encoder():
         assert torch.equal(v, head_before[k]), k
     assert all(not p.requires_grad for p in fresh.encoder.parameters())
     assert all(p.requires_grad for p in fresh.head.parameters())
+
+
+def test_reference_shaped_checkpoint_loads_and_envelope_is_lightning_compatible():
+    """A checkpoint as the reference's LightningModule writes it: extra non-network tensors (criterion.weight with
+    loss_balance_scheme=even), the Lightning envelope keys; and this repo's own files carry the same envelope."""
+    from sparseeventid_b200.trainer import checkpoint_dict, restore_checkpoint
+    import pytest
+    _, trained = _make_trainer(seed=5)
+    _, fresh = _make_trainer(seed=6)
+    ck = checkpoint_dict(trained, global_step=50, epoch=1)
+    for k in ("pytorch-lightning_version", "epoch", "global_step", "loops", "callbacks", "state_dict", "optimizer_states",
+              "lr_schedulers"):
+        assert k in ck, k
+    ref_like = dict(ck)
+    ref_like["state_dict"] = dict(ck["state_dict"])
+    ref_like["state_dict"]["criterion.weight"] = torch.ones(3)              # not part of encoder / head
+    ref_like["hyper_parameters"] = {"anything": 1}
+    assert restore_checkpoint(fresh, ref_like) == 50
+    for (k, a), (_, b) in zip(trained.state_dict().items(), fresh.state_dict().items()):
+        assert torch.equal(a, b), k
+    broken = dict(ck)
+    broken["state_dict"] = {k: v for k, v in ck["state_dict"].items() if "running_mean" not in k}
+    with pytest.raises(KeyError):
+        restore_checkpoint(fresh, broken)

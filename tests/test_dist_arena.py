@@ -95,3 +95,23 @@ def test_arena_single_process_is_plain_backward():
     for a, b in zip(model.parameters(), ref.parameters()):
         assert torch.allclose(a.grad, b.grad)
         assert a.grad.data_ptr() >= arena.flat.data_ptr()      # gradients live in the flat arena
+
+
+def test_arena_rebinds_gradients_after_zero_grad_set_to_none():
+    """optimizer.zero_grad() defaults to set_to_none=True: the next arena.zero() must point .grad back into the arena."""
+    import torch
+    from sparseeventid_b200.trainer import FlatGradArena
+    lin = torch.nn.Linear(4, 3)
+    arena = FlatGradArena(list(lin.parameters()))
+    opt = torch.optim.SGD(lin.parameters(), lr=0.1)
+    arena.zero()
+    lin(torch.ones(2, 4)).sum().backward()
+    assert float(arena.flat.abs().sum()) > 0
+    opt.zero_grad()                                         # set_to_none=True
+    assert lin.weight.grad is None
+    arena.zero()
+    assert lin.weight.grad is not None and lin.weight.grad.data_ptr() >= arena.flat.data_ptr()
+    lin(torch.ones(2, 4)).sum().backward()
+    assert float(arena.flat.abs().sum()) > 0
+    lo, hi = arena.flat.data_ptr(), arena.flat.data_ptr() + 4 * arena.flat.numel()
+    assert all(lo <= p.grad.data_ptr() < hi for p in lin.parameters())
