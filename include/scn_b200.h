@@ -117,6 +117,15 @@ size_t scn_strided_workspace(int64_t n);
 int scn_strided_rulebook(const uint64_t* keys_in, int64_t n, int s0, int s1, int s2,
                          uint64_t* keys_out, int32_t* out_row_of_in, int32_t* off_of_in,
                          int32_t* n_out_dev, void* workspace, size_t workspace_bytes, void* stream);
+/* The same rulebook through the coordinate hash (what the modules use): output rows are numbered in FIRST-APPEARANCE
+ * order over the input rows (SparseConvNet creates output rows on first touch), keys_out[0..n_out) is in that order,
+ * and table_keys / table_vals (capacity >= scn_hash_capacity(n)) receive the coarse level's hash table.
+ * workspace: scn_strided_hash_workspace(n) bytes. */
+size_t scn_strided_hash_workspace(int64_t n);
+int scn_strided_rulebook_hash(const uint64_t* keys_in, int64_t n, int s0, int s1, int s2,
+                              uint64_t* table_keys, int32_t* table_vals, int64_t capacity,
+                              uint64_t* keys_out, int32_t* out_row_of_in, int32_t* off_of_in,
+                              int32_t* n_out_dev, void* workspace, size_t workspace_bytes, void* stream);
 /* Neighbour tables of a strided rulebook: down[k][q] = input row with offset k under output q
  * (K x n_out_pad, used by Convolution fwd / Deconvolution dgrad) and up[k][p] = output row of
  * input p if its offset is k (K x n_in_pad, used by Convolution dgrad / Deconvolution fwd). */

@@ -35,6 +35,8 @@ SIGNATURES = {
     "scn_subm_rulebook": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p, _i64, _p]),
     "scn_strided_workspace": (_sz, [_i64]),
     "scn_strided_rulebook": (_i, [_p, _i64, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
+    "scn_strided_hash_workspace": (_sz, [_i64]),
+    "scn_strided_rulebook_hash": (_i, [_p, _i64, _i, _i, _i, _p, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "scn_strided_tables": (_i, [_p, _p, _i64, _i, _p, _i64, _p, _i64, _p]),
     "scn_rulebook_workspace": (_sz, [_i, _i64]),
     "scn_rulebook_count": (_i, [_p, _i, _i64, _i64, _p, _p]),

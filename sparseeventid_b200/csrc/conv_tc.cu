@@ -67,6 +67,12 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
   return d;
 }
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, A and B K-major, M=128, N=n
+// base + 16 * units as ONE instruction (IMAD.WIDE.U32 with a 64-bit addend)
+__device__ __forceinline__ const unsigned char* mad_wide16(uint32_t units, const unsigned char* base) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(units), "l"((uint64_t)(uintptr_t)base));
+  return reinterpret_cast<const unsigned char*>((uintptr_t)r);
+}
 __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
@@ -84,6 +90,7 @@ struct Params {
   int num_tiles;
   int NM;                       // active MMA-issuing warps = min(T, MMA_WARPS)
   int nbuf;                     // 2: groups alternate between the TMEM halves (T*n_out <= 256); 1: one group uses all 512 columns
+  int ksplit;                   // NM == 2 only: a CTA that owns a single tile splits its stages over the two classes (see kernel)
   unsigned long long* dbg;      // optional timeline buffer (scn_tc_debug_timeline): CTA 0 records clock64() marks
   int exp;                      // -DSCN_TC_TIMELINE builds only: timing experiments with WRONG results (SCN_B200_TC_EXP):
                                 // 1 no gather copies, 2 no MMAs, 4 no output stores
@@ -112,7 +119,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   unsigned char* tail = gbase + (size_t)SA * A_BYTES + (size_t)SB * b_bytes + 8 * NBAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail);
   uint32_t* amask = reinterpret_cast<uint32_t*>(tail + 16);                    // [MAX_A][8], 16-byte aligned
-  unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][LIST_BYTES]
+  unsigned char* lists = tail + 16 + MAX_A * MASK_BYTES;                       // [PROD_WARPS][2][LIST_BYTES]
 
   // warp index through a broadcast shuffle: the compiler then knows it is warp-uniform (role branches, barrier
   // addresses and slot numbers stay in uniform registers instead of per-lane copies with R2UR waterfalls)
@@ -134,6 +141,21 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   constexpr int exp_flags = 0;
 #endif
 
+  // This CTA's contiguous range of tiles [tile_lo, tile_hi): an even split of the tiles over the grid, cut into groups
+  // of T tiles (only the last group of a CTA can be partial; its missing tiles are not processed by anybody).
+  const int T = p.T;
+  const int tile_lo = (int)(((int64_t)p.num_tiles * blockIdx.x) / gridDim.x);
+  const int tile_hi = (int)(((int64_t)p.num_tiles * (blockIdx.x + 1)) / gridDim.x);
+  const int my_tiles = tile_hi - tile_lo;
+  const int my_groups = (my_tiles + T - 1) / T;
+  auto tiles_in_group = [&](int g) { return my_tiles - g * T < T ? my_tiles - g * T : T; };
+  const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // offsets (offset pairs) per tile
+  const int Q = NSTEP * NCH;                                // stages per tile
+  // K-split: a CTA with ONE tile (the deep levels: fewer tiles than SMs) would run all its stages through one issuing
+  // warp, a serial chain of ~800 cycles per stage.  With two classes the stages are dealt q = 0, 2, 4, ... / 1, 3, 5, ...
+  // to two issuing warps with separate TMEM accumulators (columns 0 and n_out), which the epilogue adds.
+  const bool ksplit = p.ksplit != 0 && p.NM == 2 && my_tiles == 1;
+
   if (warp == WARP_MMA) {
     if (lane == 0) {
       for (int s = 0; s < SA; ++s) {
@@ -142,7 +164,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       }
       for (int s = 0; s < SB; ++s) {
         mbar_init(bfull(s), 1);                   // the loader's expect_tx arrival (+ complete_tx bytes)
-        mbar_init(bempty(s), p.NM);               // one tcgen05.commit per issuing warp
+        mbar_init(bempty(s), ksplit ? 1 : p.NM);  // one tcgen05.commit per issuing warp that consumes the tile
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(accf(b), p.NM);
@@ -159,17 +181,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // This CTA's contiguous range of tiles [tile_lo, tile_hi): an even split of the tiles over the grid, cut into groups
-  // of T tiles (only the last group of a CTA can be partial; its missing tiles are not processed by anybody).
-  const int T = p.T;
-  const int tile_lo = (int)(((int64_t)p.num_tiles * blockIdx.x) / gridDim.x);
-  const int tile_hi = (int)(((int64_t)p.num_tiles * (blockIdx.x + 1)) / gridDim.x);
-  const int my_tiles = tile_hi - tile_lo;
-  const int my_groups = (my_tiles + T - 1) / T;
-  auto tiles_in_group = [&](int g) { return my_tiles - g * T < T ? my_tiles - g * T : T; };
-  const int NSTEP = PAIR ? (p.K + 1) / 2 : p.K;            // offsets (offset pairs) per tile
-  const int Q = NSTEP * NCH;                                // stages per tile
 
   // Classes: tile t of a group belongs to class t mod NM (NM = 1, 2 or 4).  A class is an independent pipeline: ONE issuing
   // warp, NGRP / NM producer groups and a private ring of SA / NM A slots.  Every slot therefore has a single consumer
@@ -194,7 +205,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     constexpr int LPI = PAIR ? 4 : 8;                    // lanes per item (a 128-byte row, or a 64-byte half row)
     constexpr int IPP = 32 / LPI;                        // items per pass
     const int chunk = lane % LPI, isub = lane / LPI;
-    int2* list = reinterpret_cast<int2*>(lists + pw * LIST_BYTES);   // .x source row offset / 16 B (-1: zeros), .y smem address
+    // list items: .x source row offset / 16 B (-1: zeros), .y smem address
     const uint32_t row_vec = (uint32_t)p.n_in >> 3;      // 16-byte units per feature row (list offsets are in these units)
     const int last_chunks = p.last_kc >> 3;
     const uint32_t lt = (1u << lane) - 1u;
@@ -203,50 +214,66 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     const uint32_t myrow = 32u * (uint32_t)wq + (uint32_t)lane;
     const uint32_t drow = a_base + (myrow << 7) + ((myrow & 7u) << 4);
 
-    // cursor over the class's stages: tile t (= cls, cls + NM, ...) of stage q of group g
-    int t = cls, q = 0, g = 0, tv = my_groups > 0 ? tiles_in_group(0) : 0;
+    // cursor over the class's stages: tile t (= cls, cls + NM, ...) of stage q (chunk cc of its offset) of group g;
+    // qptr -> this lane's entry of the stage's (first) offset in tile 0 of the group: the address of a fetch is one
+    // IMAD.WIDE (the 64-bit index arithmetic written out per stage was 41 of a quarter stage's 187 instructions)
+    int t = cls, q = 0, cc = 0, g = 0, tv = my_groups > 0 ? tiles_in_group(0) : 0;
+    const int32_t* gptr = p.nbr + (int64_t)tile_lo * BM + myrow;
+    const int32_t* qptr = gptr;
+    const int64_t qstride = (int64_t)p.n_pad * (PAIR ? 2 : 1);
+    auto next_q = [&]() {
+      ++q;
+      if (++cc == NCH) { cc = 0; qptr += qstride; }
+    };
     auto step = [&]() {
+      if (ksplit) {                                      // this class's stages: q = cls, cls + 2, ... of the only tile
+        next_q(); next_q();
+        if (q >= Q) { g = my_groups; tv = 0; }
+        return;
+      }
       t += NM;
       if (t >= tv) {
         t = cls;
-        if (++q == Q) { q = 0; ++g; tv = g < my_groups ? tiles_in_group(g) : 0; }
+        next_q();
+        if (q == Q) {
+          q = 0; ++g;
+          gptr += (int64_t)T * BM;
+          qptr = gptr;
+          tv = g < my_groups ? tiles_in_group(g) : 0;
+        }
       }
     };
     // only the last group of a CTA can be partial: once the class has no tile in a group it has no stage left
-    auto valid = [&]() { return g < my_groups && cls < tv; };
+    auto valid = [&]() { return g < my_groups && (ksplit ? q < Q : cls < tv); };
+    if (ksplit) {
+      t = 0;
+      if (cls == 1) next_q();
+    }
     for (int i = 0; i < sub; ++i)
       if (valid()) step();
     // Neighbour indices are fetched TWO stages ahead (the cursor runs ahead of the stage being gathered): one stage of
-    // lead (~500 cycles of this warp's own work) does not cover an L2 round trip under load, and the stall at the
-    // ballot below was ~400 of the ~1300 cycles a stage cost its producer warp (profiles/r02b_tc_timeline.txt).
-    // A fetch returns the stage's q (-1: no stage left), so the cursor never has to be rewound.
+    // lead (~500 cycles of this warp's own work) does not cover an L2 round trip under load.  A fetch returns the
+    // stage's (q << 2 | cc), or -1 when no stage is left, so the cursor never has to be rewound.
     auto fetch = [&](int& jl_, int& jh_, int& q_) {
       q_ = -1; jl_ = -1; jh_ = -1;
       if (valid()) {
-        const int stp = PAIR ? q : q / NCH;
-        const int64_t tile = (int64_t)tile_lo + (int64_t)g * T + t;
-        const int k0 = PAIR ? 2 * stp : stp;
-        const int32_t* src = p.nbr + (int64_t)k0 * p.n_pad + tile * BM + myrow;
+        const int32_t* src = qptr + t * BM;
         jl_ = ldg_nc32(src);
-        if (PAIR && (k0 + 1 < p.K)) jh_ = ldg_nc32(src + p.n_pad);
-        q_ = q;
+        if (PAIR && (2 * q + 1 < p.K)) jh_ = ldg_nc32(src + p.n_pad);
+        q_ = (q << 2) | cc;
         for (int i = 0; i < gpc; ++i) step();
       }
     };
 
-    int jl, jh, qc, jl1, jh1, q1;
-    fetch(jl, jh, qc);
-    fetch(jl1, jh1, q1);
     int ls = sub;                                        // slot within the class ring (sub < gpc <= spc)
     uint32_t round = 0;
     int it = 0;
-    while (qc >= 0) {
+    auto do_stage = [&](const int jl, const int jh, const int qc) {
       if (wq == 0) mark(grp, it, 0);
-      int jl2, jh2, q2;
-      fetch(jl2, jh2, q2);                               // two stages ahead
+      int2* list = reinterpret_cast<int2*>(lists + (pw * 2 + (it & 1)) * LIST_BYTES);   // two list buffers per warp, alternating
       const int slot = cls * spc + ls;
-      const int cc = PAIR ? 0 : qc % NCH;
-      const bool full = (qc == 0);                       // first stage of a tile: unmasked MMA, every row written
+      const int ccur = qc & 3;                           // 64-channel chunk of the offset
+      const bool full = qc < (ksplit ? 8 : 4);           // first stage of an accumulator (q == 0; K-split: q < 2): unmasked MMA, every row written
       const uint32_t dst = drow + (uint32_t)slot * A_BYTES;
       // ---- live rows -> list (full stage: every row, missing ones as zeros) ----------------------------------
       const uint32_t bl = __ballot_sync(0xffffffffu, jl >= 0);
@@ -257,14 +284,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         if (PAIR) list[32 + lane] = make_int2(jh >= 0 ? (int)((uint32_t)jh * row_vec) : -1, (int)(dst ^ 0x40u));
         nlive = PAIR ? 64 : 32;
       } else {
-        if (jl >= 0) list[__popc(bl & lt)] = make_int2((int)((uint32_t)jl * row_vec), (int)dst);
+        const int2 el = make_int2((int)((uint32_t)jl * row_vec), (int)dst);
+        const int2 eh = make_int2((int)((uint32_t)jh * row_vec), (int)(dst ^ 0x40u));
+        if (jl >= 0) list[__popc(bl & lt)] = el;
         nlive = __popc(bl);
         if (PAIR) {
-          if (jh >= 0) list[nlive + __popc(bh & lt)] = make_int2((int)((uint32_t)jh * row_vec), (int)(dst ^ 0x40u));
+          if (jh >= 0) list[nlive + __popc(bh & lt)] = eh;
           nlive += __popc(bh);
         }
+        // pad the list to whole passes with copies of its last item (copying a row twice is harmless): the gather
+        // loop below then needs no per-item predicates (they were a third of its instructions)
+        if (nlive & (IPP - 1)) {
+          const bool from_hi = PAIR && bh != 0u;
+          const int top = 31 - __clz(from_hi ? bh : bl);
+          const int lx = __shfl_sync(0xffffffffu, from_hi ? eh.x : el.x, top);
+          const int ly = __shfl_sync(0xffffffffu, from_hi ? eh.y : el.y, top);
+          const int padded = (nlive + IPP - 1) & ~(IPP - 1);
+          if (nlive + lane < padded) list[nlive + lane] = make_int2(lx, ly);
+        }
       }
-      __syncwarp();
+      __syncwarp();                                      // the list is complete (its buffer is rewritten two stages later)
       if (wq == 0) mark(grp, it, 1);
 
       // the MMAs that read this slot's previous stage have retired
@@ -275,22 +314,19 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         if (PAIR) amask[slot * 8 + 4 + wq] = ~bh;
       }
       const int npass = (nlive + IPP - 1) / IPP;         // <= 8
-      const bool lane_on = PAIR ? true : chunk < (cc == NCH - 1 ? last_chunks : 8);
-      const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)cc * 128u + csw);
+      const bool lane_on = PAIR ? true : chunk < (ccur == NCH - 1 ? last_chunks : 8);
+      const unsigned char* src0 = reinterpret_cast<const unsigned char*>(p.in) + ((uint32_t)ccur * 128u + csw);
       if (lane_on && !(exp_flags & 1)) {
         if (!full) {
-          // hot path per pass: LDS.64, IMAD.WIDE (source address), LOP3 (destination), LDGSTS
-          for (int p0 = 0; p0 < npass; p0 += 4) {        // 4 list entries are read before their copies are issued
+          // hot path per pass: LDS.64, one 32x32+64 multiply-add (source address), LOP3 (destination), LDGSTS
+          for (int p0 = 0; p0 < npass; p0 += 4) {        // up to 4 list entries are read before their copies are issued
             int2 e[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int item = (p0 + u) * IPP + isub;
-              e[u] = make_int2(0, 0);
-              if (item < nlive) e[u] = list[item];
-            }
+            for (int u = 0; u < 4; ++u)
+              if (p0 + u < npass) e[u] = list[(p0 + u) * IPP + isub];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-              if (e[u].y != 0) cp_async16((uint32_t)e[u].y ^ csw, src0 + ((uint64_t)(uint32_t)e[u].x << 4), 16u);
+              if (p0 + u < npass) cp_async16((uint32_t)e[u].y ^ csw, mad_wide16((uint32_t)e[u].x, src0), 16u);
           }
         } else {
           // first stage of a tile: every row is written, missing neighbours as zeros (src-size 0 reads nothing)
@@ -298,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
           for (int pass = 0; pass < 8; ++pass) {
             const int2 e = list[pass * IPP + isub];
             const bool live = e.x != -1;
-            cp_async16((uint32_t)e.y ^ csw, src0 + ((uint64_t)(live ? (uint32_t)e.x : 0u) << 4), live ? 16u : 0u);
+            cp_async16((uint32_t)e.y ^ csw, mad_wide16(live ? (uint32_t)e.x : 0u, src0), live ? 16u : 0u);
           }
         }
       }
@@ -306,13 +342,23 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       // have completed.  Lane 0's ordinary arrival (release) publishes the mask words it stored above.
       cp_async_arrive_noinc(afull(slot));
       if (lane == 0) mbar_arrive(afull(slot));
-      __syncwarp();                                      // all lanes have read the list (rewritten next iteration)
       if (wq == 0) mark(grp, it, 3);
       ++it;
       ls += gpc;
       if (ls >= spc) { ls -= spc; ++round; }
-      jl = jl1; jh = jh1; qc = q1;
-      jl1 = jl2; jh1 = jh2; q1 = q2;
+    };
+
+    // Indices are fetched two stages ahead.  (Two stages per loop iteration, so that the register hand-over below never
+    // waits for a load in flight, was measured and is slower: 76 -> 89 us at 495 k rows x 32 channels.)
+    int jlA, jhA, qA, jlB, jhB, qB;
+    fetch(jlA, jhA, qA);
+    fetch(jlB, jhB, qB);
+    while (qA >= 0) {
+      int jlC, jhC, qC;
+      fetch(jlC, jhC, qC);
+      do_stage(jlA, jhA, qA);
+      jlA = jlB; jhA = jhB; qA = qB;
+      jlB = jlC; jhB = jhC; qB = qC;
     }
   } else if (warp == WARP_BLOAD) {
     // ================================ weight-tile loader (1 elected lane, bulk async copies) ==
@@ -347,6 +393,70 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
       int ls = 0;                                                     // this class's next stage: slot m * spc + ls ...
       uint32_t around = 0;                                            // ... in round `around` of that slot
       int it = 0;
+      // one stage: wait for its four quarters (and their masks), issue its MMAs into columns `col`, free the A slot
+      auto issue_stage = [&](int q, uint32_t col, uint64_t db, bool first) {
+        const int cc = PAIR ? 0 : q % NCH;
+        const int step = PAIR ? q : q / NCH;
+        // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
+        const int nk = PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4);
+        const int aslot = m * spc + ls;
+        mark(4 + m, it, 0);
+        mbar_wait(afull(aslot), around & 1u);                // all four quarters of the stage have landed (and their masks)
+        mark(4 + m, it, 1);
+        tc_fence_after();
+        // disable-output-lane masks published by the stage's producers: bit r set <=> output row r has no
+        // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
+        // them provably warp-uniform so they are moved to uniform registers once.
+        uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+        if (!first) {
+          const uint4 mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
+          m0 = __ballot_sync(0xffffffffu, (mw.x >> lane) & 1u);
+          m1 = __ballot_sync(0xffffffffu, (mw.y >> lane) & 1u);
+          m2 = __ballot_sync(0xffffffffu, (mw.z >> lane) & 1u);
+          m3 = __ballot_sync(0xffffffffu, (mw.w >> lane) & 1u);
+          if (PAIR) {
+            const uint4 hw = *reinterpret_cast<const uint4*>(amask + aslot * 8 + 4);
+            h0 = __ballot_sync(0xffffffffu, (hw.x >> lane) & 1u);
+            h1 = __ballot_sync(0xffffffffu, (hw.y >> lane) & 1u);
+            h2 = __ballot_sync(0xffffffffu, (hw.z >> lane) & 1u);
+            h3 = __ballot_sync(0xffffffffu, (hw.w >> lane) & 1u);
+          }
+        }
+        const uint64_t da = da0 + (uint64_t)((uint32_t)aslot * (A_BYTES >> 4));
+        const uint32_t tmem_d = tmem_base + col;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            if (kk < nk && !(exp_flags & 2)) {
+              const bool hi = PAIR && kk >= 2;
+              umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (!first || kk > 0) ? 1u : 0u,
+                          hi ? h0 : m0, hi ? h1 : m1, hi ? h2 : m2, hi ? h3 : m3);
+            }
+          }
+          umma_commit(aempty(aslot));                                  // frees the A slot when these MMAs retire
+        }
+        __syncwarp();
+        mark(4 + m, it, 2);
+        ++it;
+        if (++ls == spc) { ls = 0; ++around; }
+      };
+      if (ksplit) {
+        // one tile, one group: this warp issues the stages q = m, m + 2, ... into its own accumulator (columns m * n_out);
+        // a weight tile is consumed by one class only (SB is even: a B slot always belongs to the same class)
+        mbar_wait(acce(0), 1u);
+        tc_fence_after();
+        bslot = m;
+        for (int q = m; q < Q; q += 2) {
+          mbar_wait(bfull(bslot), bround & 1u);
+          issue_stage(q, (uint32_t)(m * p.n_out), db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4), q < 2);
+          if (elect_one()) umma_commit(bempty(bslot));
+          __syncwarp();
+          bslot += 2;
+          if (bslot >= SB) { bslot -= SB; ++bround; }
+        }
+        if (elect_one()) umma_commit(accf(0));
+        __syncwarp();
+      } else
       for (int g = 0; g < my_groups; ++g) {
         const int buf = nbuf == 2 ? (g & 1) : 0;
         const uint32_t use = (uint32_t)(nbuf == 2 ? (g >> 1) : g);    // how many times this buffer has been used before
@@ -354,56 +464,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
         mbar_wait(acce(buf), (use & 1u) ^ 1u);                        // epilogue has drained this accumulator buffer
         tc_fence_after();
         for (int q = 0; q < Q; ++q) {
-          const int cc = PAIR ? 0 : q % NCH;
-          const int step = PAIR ? q : q / NCH;
           mark(10 + m, g * Q + q, 0);
           mbar_wait(bfull(bslot), bround & 1u);
           mark(10 + m, g * Q + q, 1);
           const uint64_t db = db0 + (uint64_t)(((uint32_t)bslot * b_bytes) >> 4);
-          // PAIR with an odd K: the last stage holds one offset only, its upper 32 channels are never written
-          const int nk = PAIR ? ((2 * step + 1 < p.K) ? 4 : 2) : ((cc == NCH - 1 ? p.last_kc : KC) >> 4);
-          for (int t = m; t < tv; t += NM) {
-            const int aslot = m * spc + ls;
-            mark(4 + m, it, 0);
-            mbar_wait(afull(aslot), around & 1u);            // all four quarters of the stage have landed (and their masks)
-            mark(4 + m, it, 1);
-            tc_fence_after();
-            // disable-output-lane masks published by the stage's producers: bit r set <=> output row r has no
-            // neighbour at this offset (its A row is stale).  Every lane loads the same words; the ballots make
-            // them provably warp-uniform so they are moved to uniform registers once.
-            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0, h0 = 0, h1 = 0, h2 = 0, h3 = 0;
-            if (q > 0) {
-              const uint4 mw = *reinterpret_cast<const uint4*>(amask + aslot * 8);
-              m0 = __ballot_sync(0xffffffffu, (mw.x >> lane) & 1u);
-              m1 = __ballot_sync(0xffffffffu, (mw.y >> lane) & 1u);
-              m2 = __ballot_sync(0xffffffffu, (mw.z >> lane) & 1u);
-              m3 = __ballot_sync(0xffffffffu, (mw.w >> lane) & 1u);
-              if (PAIR) {
-                const uint4 hw = *reinterpret_cast<const uint4*>(amask + aslot * 8 + 4);
-                h0 = __ballot_sync(0xffffffffu, (hw.x >> lane) & 1u);
-                h1 = __ballot_sync(0xffffffffu, (hw.y >> lane) & 1u);
-                h2 = __ballot_sync(0xffffffffu, (hw.z >> lane) & 1u);
-                h3 = __ballot_sync(0xffffffffu, (hw.w >> lane) & 1u);
-              }
-            }
-            const uint64_t da = da0 + (uint64_t)((uint32_t)aslot * (A_BYTES >> 4));
-            const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u + (uint32_t)(t * p.n_out);
-            if (elect_one()) {
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                if (kk < nk && !(exp_flags & 2)) {
-                  const bool hi = PAIR && kk >= 2;
-                  umma_masked(tmem_d, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (q > 0 || kk > 0) ? 1u : 0u,
-                              hi ? h0 : m0, hi ? h1 : m1, hi ? h2 : m2, hi ? h3 : m3);
-                }
-              }
-              umma_commit(aempty(aslot));                              // frees the A slot when these MMAs retire
-            }
-            __syncwarp();
-            mark(4 + m, it, 2);
-            ++it;
-            if (++ls == spc) { ls = 0; ++around; }
-          }
+          for (int t = m; t < tv; t += NM) issue_stage(q, (uint32_t)buf * 256u + (uint32_t)(t * p.n_out), db, q == 0);
           if (elect_one()) umma_commit(bempty(bslot));
           __syncwarp();
           if (++bslot == SB) { bslot = 0; ++bround; }
@@ -414,6 +479,33 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
     }
   } else if (warp < EPI_WARPS) {
     // ================================ epilogue (warps 0..3) ==================================
+    if (ksplit) {
+      // one tile whose two partial accumulators (columns 0.. and n_out..) are added on the way out
+      mbar_wait_sleep(accf(0), 0u);
+      tc_fence_after();
+      const int64_t row = (int64_t)tile_lo * BM + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+      for (int c0 = 0; c0 < p.n_out; c0 += 16) {
+        uint32_t a[16], b[16];
+        tmem_ld16x2(taddr + (uint32_t)c0, taddr + (uint32_t)(p.n_out + c0), a, b);
+        if (row < p.n_rows && !(exp_flags & 4)) {
+          uint4* dst = reinterpret_cast<uint4*>(p.out + row * p.n_out + c0);
+#pragma unroll
+          for (int gq = 0; gq < 2; ++gq) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              f[e] = __uint_as_float(a[gq * 8 + e]) + __uint_as_float(b[gq * 8 + e]) +
+                     (p.bias ? __ldg(p.bias + c0 + gq * 8 + e) : 0.f);
+            uint4 u;
+            u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+            u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+            dst[gq] = u;
+          }
+        }
+      }
+      tc_fence_before();
+    } else
     for (int g = 0; g < my_groups; ++g) {
       const int buf = p.nbuf == 2 ? (g & 1) : 0;
       if (warp == 0) mark(9, g, 0);
@@ -531,6 +623,14 @@ static int env_int(const char* name) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : 0;
 }
+static bool g_ksplit_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SCN_B200_TC_KSPLIT");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 static int g_knob[4] = {-1, -1, -1, -1};      // grid, T, SA, SB: -1 = read the environment on first use
 // developer entry for the sweep tools (like scn_tc_debug_timeline: not part of the product ABI): 0 = automatic
 extern "C" void scn_tc_debug_knobs(int grid, int t, int sa, int sb) {
@@ -587,15 +687,27 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   }
   p.T = T;
   p.NM = T >= 4 ? 4 : (T >= 2 ? 2 : 1);         // classes (issuing warps): a power of two that divides NGRP
+  // K-split (see the kernel): CTAs that own a single tile deal its stages to two classes.  Possible when a launch has two
+  // classes anyway (T == 2 or 3: the deep levels with one or two tiles per CTA) or one tile per CTA and room for a second
+  // accumulator; SCN_B200_TC_KSPLIT=0 turns it off.
+  p.ksplit = 0;
+  const int stages_per_tile = (tc_pair(n_in) ? (K + 1) / 2 : K) * nch;
+  if (g_ksplit_enabled() && stages_per_tile >= 2) {          // both accumulators must receive a first stage
+    if (p.NM == 1 && per_cta == 1 && 2 * n_out <= 512) { p.NM = 2; p.nbuf = 1; p.ksplit = 1; }
+    else if (p.NM == 2) p.ksplit = 1;
+  }
   const uint32_t b_bytes = (uint32_t)n_out * 128u;
   const bool pair = tc_pair(n_in);
   constexpr int NBAR = 2 * tc::MAX_A + 2 * tc::MAX_B + 4;
   const uint32_t fixed = 1024u + 8u * NBAR + 16u + (uint32_t)tc::MAX_A * tc::MASK_BYTES +
-                         (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES + 16u;
+                         2u * (uint32_t)tc::PROD_WARPS * tc::LIST_BYTES + 16u;
   const uint32_t budget = 226u * 1024u - fixed;
   // A ring: a multiple of NGRP slots (every class ring then is a multiple of its producer groups: parity-safe), 8 by
   // default (measured: depth beyond 6 buys nothing); the weight ring gets the rest, up to MAX_B tiles
   int SA = 8;
+  // K-split launches (one or two tiles per CTA, wide layers): the weight tiles (n_out x 128 B per stage, consumed by one
+  // class each) need the depth, the A ring does not (measured: 4 slots == 8 slots at these shapes)
+  if (p.ksplit && per_cta <= 2) SA = 4;
   if (force_sa > 0) SA = force_sa;
   SA = SA / tc::NGRP * tc::NGRP;
   if (SA > tc::MAX_A) SA = tc::MAX_A;
@@ -605,6 +717,7 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   int SB = (int)((budget - (uint32_t)SA * tc::A_BYTES) / b_bytes);
   if (SB > tc::MAX_B) SB = tc::MAX_B;
   if (force_sb >= 2 && force_sb < SB) SB = force_sb;
+  if (p.ksplit && (SB & 1)) --SB;                // K-split: a B slot must always belong to the same class
   p.SA = SA;
   p.SB = SB;
   const size_t smem = (size_t)fixed + (size_t)SA * tc::A_BYTES + (size_t)SB * b_bytes;

@@ -202,6 +202,45 @@ extern "C" int scn_strided_rulebook(const uint64_t* keys_in, int64_t n, int s0, 
   return SCN_OK;
 }
 
+// ---- the same rulebook through the coordinate hash (the path the modules use) --------------------------------------
+// Output sites are the distinct coarse keys; they are found and NUMBERED IN FIRST-APPEARANCE ORDER over the input rows
+// by the InputLayer machinery (hash insert with smallest-index-wins, flag, scan), which is SparseConvNet's own order
+// (output rows are created on first touch) and leaves behind the coarse level's hash table, so the next level needs no
+// separate build.  Replaces a 64-bit radix sort (8 onesweep passes per level, ~135 us even for 7 k sites).
+namespace {
+__global__ void k_coarse_keys_off(const uint64_t* __restrict__ keys, int64_t n, int s0, int s1, int s2,
+                                  uint64_t* __restrict__ qkeys, int32_t* __restrict__ off) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int x0, x1, x2, b;
+  key_unpack(keys[i], x0, x1, x2, b);
+  int q0 = x0 / s0, q1 = x1 / s1, q2 = x2 / s2;
+  qkeys[i] = key_pack(q0, q1, q2, b);
+  off[i] = ((x0 - q0 * s0) * s1 + (x1 - q1 * s1)) * s2 + (x2 - q2 * s2);
+}
+}  // namespace
+
+extern "C" size_t scn_strided_hash_workspace(int64_t n) {
+  return (size_t)round_up_i64(n * 8, 256) + scn_input_rules_workspace(n) + 256;
+}
+
+extern "C" int scn_strided_rulebook_hash(const uint64_t* keys_in, int64_t n, int s0, int s1, int s2, uint64_t* table_keys,
+                                         int32_t* table_vals, int64_t capacity, uint64_t* keys_out,
+                                         int32_t* out_row_of_in, int32_t* off_of_in, int32_t* n_out_dev, void* workspace,
+                                         size_t workspace_bytes, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (s0 < 1 || s1 < 1 || s2 < 1 || !n_out_dev || !table_keys || !table_vals) return SCN_ERR_ARG;
+  if (n > 0 && (!workspace || workspace_bytes < scn_strided_hash_workspace(n))) return SCN_ERR_WORKSPACE;
+  uint64_t* qkeys = (uint64_t*)workspace;
+  char* ws2 = (char*)workspace + round_up_i64(n * 8, 256);
+  if (n > 0) {
+    k_coarse_keys_off<<<grid_for(n, 256), 256, 0, s>>>(keys_in, n, s0, s1, s2, qkeys, off_of_in);
+    SCN_LAUNCH_CHECK();
+  }
+  return scn_input_layer_rules(qkeys, n, table_keys, table_vals, capacity, out_row_of_in, keys_out, n_out_dev, ws2,
+                               n > 0 ? workspace_bytes - (size_t)round_up_i64(n * 8, 256) : 0, stream);
+}
+
 extern "C" int scn_strided_tables(const int32_t* out_row_of_in, const int32_t* off_of_in, int64_t n_in, int K,
                                   int32_t* nbr_down, int64_t n_out_pad, int32_t* nbr_up, int64_t n_in_pad,
                                   void* stream) {

@@ -74,7 +74,10 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 
 // NA / NB: 64-channel blocks of a stage's A (x rows) / B (dout rows) operand = ceil(Cin / 64), ceil(Cout / 64)
 // HALF: Cin == Cout == 32, rows are 64 bytes: 4 lanes per row and 8 rows per pass instead of 8 lanes / 4 rows
-template <int NA, int NB, bool HALF>
+// TEAM (wide layers, NA + NB >= 4: a stage is 32-48 KB and only 4-6 slots fit): producers work in TEAMS of two warps.
+// Both warps of a team walk the same blocks and build the same pair ring (private copies: no communication), and at
+// emit time warp 0 copies the x rows, warp 1 the dout rows of the stage; a producer unit below is a team.
+template <int NA, int NB, bool HALF, bool TEAM>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
     if (lane == 0) {
       for (int s = 0; s < slots; ++s) {
         st_release_u32(seq + 4u * (uint32_t)s, 0u);
-        mbar_init(afull(s), 32);                 // the 32 lanes of the owning producer warp, each when its copies landed
+        mbar_init(afull(s), TEAM ? 64 : 32);     // the lanes of the owning producer warp (team), each when its copies landed
         mbar_init(aempty(s), 1);                 // one tcgen05.commit
       }
       for (int w = 0; w < PROD_WARPS; ++w) st_release_u32(done + 4u * (uint32_t)w, 0u);
@@ -129,9 +132,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // ================================ producers =============================================
-    const int pw = warp - EPI_WARPS;
+    const int wi = warp - EPI_WARPS;                        // producer warp
+    const int pw = TEAM ? (wi >> 1) : wi;                   // producer unit (warp or team): owns slots pw and pw + NPW
+    const int role = TEAM ? (wi & 1) : 0;                   // TEAM: 0 copies the x rows (A blocks), 1 the dout rows (B blocks)
     if (pw < NPW) {
-      int2* ring = rings + pw * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
+      int2* ring = rings + wi * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
       const uint32_t xvec = (uint32_t)p.Cin >> 3, dvec = (uint32_t)p.Cout >> 3;
       const uint32_t lt = (1u << lane) - 1u;
       constexpr int LPR = HALF ? 4 : 8;                     // lanes per row
@@ -165,20 +170,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
           const uint32_t dst = (sbase + (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4)) ^ csw;
           const unsigned char* xs = xsrc + ((uint64_t)(uint32_t)e.x << 4);
           const unsigned char* ds = dsrc + ((uint64_t)(uint32_t)e.y << 4);
+          if (!TEAM || role == 0) {
 #pragma unroll
-          for (int b = 0; b < NA; ++b) {                     // x row -> A blocks
-            const bool ok = live && a_ok[b];
-            cp_async16(dst + (uint32_t)b * BLK_BYTES, ok ? xs + b * 128 : xs, ok ? 16u : 0u);
+            for (int b = 0; b < NA; ++b) {                   // x row -> A blocks
+              const bool ok = live && a_ok[b];
+              cp_async16(dst + (uint32_t)b * BLK_BYTES, ok ? xs + b * 128 : xs, ok ? 16u : 0u);
+            }
           }
+          if (!TEAM || role == 1) {
 #pragma unroll
-          for (int b = 0; b < NB; ++b) {                     // dout row -> B blocks
-            const bool ok = live && b_ok[b];
-            cp_async16(dst + (uint32_t)(NA + b) * BLK_BYTES, ok ? ds + b * 128 : ds, ok ? 16u : 0u);
+            for (int b = 0; b < NB; ++b) {                   // dout row -> B blocks
+              const bool ok = live && b_ok[b];
+              cp_async16(dst + (uint32_t)(NA + b) * BLK_BYTES, ok ? ds + b * 128 : ds, ok ? 16u : 0u);
+            }
           }
         }
         cp_async_arrive_noinc(afull(slot));
         __syncwarp();
-        if (lane == 0)
+        if (lane == 0 && role == 0)                          // (TEAM: the landing barrier still needs the other warp's 32 arrivals)
           st_release_u32(seq + 4u * (uint32_t)slot, ((uint32_t)emitted + 1u) | ((((uint32_t)emitted >> 1) & 1u) << 31));
         head = (head + take) & (RING - 1);
         pending -= take;
@@ -214,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
         while (pending >= PAIRS) emit(PAIRS);
       }
       if (pending > 0) emit(pending);
-      if (lane == 0) st_release_u32(done + 4u * (uint32_t)pw, (uint32_t)emitted + 1u);
+      if (lane == 0 && role == 0) st_release_u32(done + 4u * (uint32_t)pw, (uint32_t)emitted + 1u);
     }
   } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ============================================
@@ -337,6 +346,8 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
   if (slots > wg::MAX_SLOTS) slots = wg::MAX_SLOTS;
   slots &= ~1;
   if (slots < 2) return SCN_ERR_UNSUPPORTED;
+  const bool team = (p.nca + p.ncb) >= 4;
+  if (team && slots > wg::PROD_WARPS) slots = wg::PROD_WARPS & ~1;   // a team (two warps) per pair of slots
   p.slots = slots;
   p.npw = slots / 2;
   // CTAs: two full waves (one CTA per SM at a time); the centre offset of an odd-sized (submanifold) table holds
@@ -345,7 +356,12 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
   // ~1000 pairs or more (about 30% of the K*n table entries are pairs in the reference's networks).
   int target = 2 * kNumSMs;
   {
-    const int64_t by_work = (int64_t)((double)n_rows * K * 0.3 / 1024.0);
+    static const int pairs_per_cta = [] {                    // developer knob for sweeps: SCN_B200_WG_PAIRS=<pairs per CTA>
+      const char* e = std::getenv("SCN_B200_WG_PAIRS");
+      const int v = e ? std::atoi(e) : 0;
+      return v > 0 ? v : 1024;
+    }();
+    const int64_t by_work = (int64_t)((double)n_rows * K * 0.3 / (double)pairs_per_cta);
     if (by_work < target) target = (int)(by_work < K ? K : by_work);
   }
   const int64_t nblocks = (n_rows + 127) / 128;
@@ -375,8 +391,8 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };
-  if (Cin == 32 && Cout == 32) return launch(wg::k_wgrad_tc<1, 1, true>);
-#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b, false>)
+  if (Cin == 32 && Cout == 32) return launch(wg::k_wgrad_tc<1, 1, true, false>);
+#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b, false, ((a) + (b) >= 4)>)
   WG_CASE(1, 1); WG_CASE(1, 2); WG_CASE(1, 3); WG_CASE(1, 4);
   WG_CASE(2, 1); WG_CASE(2, 2); WG_CASE(2, 3); WG_CASE(2, 4);
   WG_CASE(3, 1); WG_CASE(3, 2); WG_CASE(3, 3); WG_CASE(3, 4);

@@ -214,7 +214,7 @@ class Metadata:
         lvl = self.levels[spatial]
         self.plan.append(("strided", spatial, filt, stride))
         with self.rulebook_stream() as rs:
-            keys_out, out_row, off = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
+            keys_out, out_row, off, table = ops.strided_rulebook(lvl.keys, pad3(stride, 1))
             if out_spatial in self.levels:
                 # coarse grid already exists (e.g. built through another path): re-index onto its rows
                 have = self.levels[out_spatial]
@@ -222,7 +222,7 @@ class Metadata:
                 out_row = remap[out_row.long()].contiguous()
                 n_out = have.n
             else:
-                new = self.add_level(out_spatial, keys_out.clone())
+                new = self.add_level(out_spatial, keys_out.clone(), table)      # the rulebook left the level's hash table behind
                 rs.publish(new.keys, new.table_keys, new.table_vals)
                 n_out = int(keys_out.shape[0])
             K = 1

@@ -387,4 +387,51 @@ class SparseToDense(nn.Module):
 
 
 class Sequential(nn.Sequential):
-    pass
+    """scn.Sequential: torch's container plus SparseConvNet's chaining `.add(module)`."""
+
+    def add(self, module):
+        self._modules[str(len(self._modules))] = module
+        return self
+
+
+class SparseGroupNorm(nn.Module):
+    """scn.SparseGroupNorm(num_groups, num_channels, eps=1e-5, affine=True) -- named by the reference's non-default
+    normalisation branches (src/networks/sparse_building_blocks.py:12,42,125,220: `encoder.normalization` = group /
+    instance / InputNorm).  SparseConvNet itself has no such class (those branches raise AttributeError on the real
+    package), so there is no upstream algorithm to restate; it is DEFINED here as torch.nn.GroupNorm restricted to the
+    active sites: per sample and channel group, mean / biased variance over (active rows of the sample) x (channels of
+    the group), then a per-channel affine.  Off the benchmarked path: segment sums with torch ops on the device (fp32),
+    no dedicated kernel."""
+
+    def __init__(self, num_groups, num_channels, eps=1e-5, affine=True):
+        super().__init__()
+        assert num_channels % num_groups == 0, "num_channels must be divisible by num_groups"
+        self.num_groups, self.num_channels, self.eps, self.affine = num_groups, num_channels, eps, affine
+        if affine:
+            self.weight = nn.Parameter(torch.ones(num_channels))
+            self.bias = nn.Parameter(torch.zeros(num_channels))
+        else:
+            self.register_parameter("weight", None)
+            self.register_parameter("bias", None)
+
+    def forward(self, input):
+        x = input.features
+        L.require_cuda(x, "SparseGroupNorm")
+        md = input.metadata
+        n, c = x.shape
+        assert c == self.num_channels
+        g, cg = self.num_groups, c // self.num_groups
+        b = (md.levels[input._sp()].keys >> 48).long()                        # sample of every active row
+        nb = max(int(md.batch_size), 1)
+        xf = x.float().view(n, g, cg)
+        cnt = torch.zeros(nb, device=x.device).index_add_(0, b, torch.ones(n, device=x.device)).clamp_min(1.0) * cg
+        mean = torch.zeros(nb, g, device=x.device).index_add_(0, b, xf.sum(2)) / cnt[:, None]
+        d = xf - mean[b][:, :, None]
+        var = torch.zeros(nb, g, device=x.device).index_add_(0, b, (d * d).sum(2)) / cnt[:, None]
+        y = (d * torch.rsqrt(var + self.eps)[b][:, :, None]).view(n, c)
+        if self.affine:
+            y = y * self.weight + self.bias
+        return _new_like(input, y.to(x.dtype))
+
+    def __repr__(self):
+        return f"SparseGroupNorm({self.num_groups}, {self.num_channels}, eps={self.eps}, affine={self.affine})"

@@ -159,24 +159,26 @@ def subm_rulebook(keys, tk, tv, cap, filt) -> torch.Tensor:
 
 
 def strided_rulebook(keys_in, stride):
-    """-> (keys_out int64 [n_out] sorted, out_row_of_in int32 [n], off_of_in int32 [n]).  One D2H sync."""
+    """-> (keys_out int64 [n_out] in first-appearance order, out_row_of_in int32 [n], off_of_in int32 [n],
+    (table_keys, table_vals, cap) = the coarse level's hash table).  One D2H sync."""
     n = keys_in.shape[0]
     dev = keys_in.device
     keys_out = torch.empty((n,), dtype=torch.int64, device=dev)
     out_row = _i32(n, dev)
     off = _i32(n, dev)
     n_out = torch.zeros((1,), dtype=torch.int32, device=dev)
-    ws_bytes = int(L.lib().scn_strided_workspace(n))
+    tk, tv, cap = new_table(n, dev)
+    ws_bytes = int(L.lib().scn_strided_hash_workspace(n))
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     p = _profiler
     e0 = p.begin() if p else None
-    L.check(L.lib().scn_strided_rulebook(L.ptr(keys_in), n, stride[0], stride[1], stride[2], L.ptr(keys_out),
-                                         L.ptr(out_row), L.ptr(off), L.ptr(n_out), L.ptr(ws), ws_bytes, L.stream()),
-            "scn_strided_rulebook")
+    L.check(L.lib().scn_strided_rulebook_hash(L.ptr(keys_in), n, stride[0], stride[1], stride[2], L.ptr(tk), L.ptr(tv), cap,
+                                              L.ptr(keys_out), L.ptr(out_row), L.ptr(off), L.ptr(n_out), L.ptr(ws), ws_bytes,
+                                              L.stream()), "scn_strided_rulebook_hash")
     if p:
         p.end(e0, kind="rulebook_strided", bytes=24.0 * n, rows=n)
     m = int(n_out.item())
-    return keys_out[:m], out_row, off
+    return keys_out[:m], out_row, off, (tk, tv, cap)
 
 
 def strided_tables(out_row, off, K, n_in, n_out):

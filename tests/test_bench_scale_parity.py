@@ -1,9 +1,10 @@
 """Parity at the BENCHMARKED configuration (bench.py's first batch: 64 synthetic dune3d events, ~5e5 active sites).
 
   * rulebooks: the neighbour tables of all six levels (3^3), the 5^3 stem and the five stride-2 maps are compared
-    BIT-EXACT with the oracle's rulebooks.  Row numbering is canonical on both sides (level 0: first appearance ==
-    input order, checked; deeper levels: ascending packed key, checked), so the table form nbr[k][out] = in IS the
-    order-normalised rulebook.
+    BIT-EXACT with the oracle's rulebooks.  Level-0 rows are the input order on both sides (checked); deeper levels are
+    numbered in first-appearance order on the GPU and by ascending key in the oracle, so the GPU tables are translated
+    row by row through the coordinate-matched permutation before the comparison: the table form nbr[k][out] = in,
+    in one numbering, IS the order-normalised rulebook.
   * one training step (forward, focal loss, backward) of the default encoder + heads on that batch:
       - "fp32" mode against the oracle in float64 ("truth"): loss / logits / encoder output / gradient norms within
         2e-3 relative (BASELINE.json north_star bar); element-wise, a gradient tensor may differ from truth by 2e-2
@@ -54,26 +55,38 @@ def test_bench_batch_rulebooks_bit_exact():
     md = x.metadata
     sp = tuple(synthetic.GRID_3D)
     assert np.array_equal(md.coords(sp).cpu().numpy(), ci)               # level 0 rows == input order
-    cur = ci
+    cur = ci                                     # oracle rows of the level
+    gmap = np.arange(ci.shape[0])                # GPU row -> oracle row (level 0: identical numbering)
+
+    def to_oracle(table, rows_map, vals_map):
+        """GPU table [K, n] (rows / entries in GPU numbering) -> the same table in the oracle's numbering."""
+        out = np.full_like(table, -1)
+        out[:, rows_map] = np.where(table >= 0, vals_map[np.maximum(table, 0)], -1)
+        return out
+
     for level in range(6):
         n = cur.shape[0]
         for filt in ([(5, 5, 5)] if level == 0 else []) + [(3, 3, 3)]:
             got = md.subm_table(sp, filt)[:, :n].cpu().numpy().astype(np.int64)
             want = rules_to_table(O.submanifold_rulebook(cur, filt), n)
-            assert np.array_equal(got, want), f"level {level} filter {filt}: neighbour table differs from the oracle rulebook"
+            assert np.array_equal(to_oracle(got, gmap, gmap), want), f"level {level} filter {filt}: neighbour table differs from the oracle rulebook"
             assert bool((md.subm_table(sp, filt)[:, n:] == -1).all())
         if level == 5:
             break
         rule = md.strided_rule(sp, (2, 2, 2), (2, 2, 2))
         out_coords, rules, out_sp = O.strided_rulebook(cur, (2, 2, 2), (2, 2, 2), sp)
         assert rule.out_spatial == out_sp and rule.n_out == out_coords.shape[0]
-        assert np.array_equal(md.coords(out_sp).cpu().numpy(), out_coords)   # ascending-key rows on both sides
+        # same output sites; the GPU numbers them in first-appearance order, the oracle by ascending key
+        gloc = md.coords(out_sp).cpu().numpy()
+        gkeys, okeys = O.pack_keys(gloc), O.pack_keys(out_coords)
+        assert np.array_equal(np.sort(gkeys), okeys)
+        gmap_next = np.searchsorted(okeys, gkeys)
         down = rule.down[:, :rule.n_out].cpu().numpy().astype(np.int64)
-        assert np.array_equal(down, rules_to_table(rules, rule.n_out)), f"level {level}: stride-2 map differs"
+        assert np.array_equal(to_oracle(down, gmap_next, gmap), rules_to_table(rules, rule.n_out)), f"level {level}: stride-2 map differs"
         up = rule.up[:, :n].cpu().numpy().astype(np.int64)
         want_up = rules_to_table([r[:, ::-1] for r in rules], n)
-        assert np.array_equal(up, want_up), f"level {level}: transposed stride-2 map differs"
-        cur, sp = out_coords, out_sp
+        assert np.array_equal(to_oracle(up, gmap, gmap_next), want_up), f"level {level}: transposed stride-2 map differs"
+        cur, sp, gmap = out_coords, out_sp, gmap_next
     assert cur.shape[0] > 1000
 
 
