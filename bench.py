@@ -73,6 +73,31 @@ def host_batch(batch, seed, dataset):
     return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
 
 
+def balanced_host_batch(batch, world, rank, seed, dataset):
+    """Event-sharded data parallelism with voxel-count balancing: the global batch of batch x world events
+    is dealt to the ranks in a snake over the events sorted by active-site count, so every rank gets the same number of
+    events AND (within ~0.2%) the same number of voxels.  Contiguous sharding of DUNE-like events leaves the heaviest of 8
+    ranks 12% above the mean, and a synchronous step runs at the pace of the heaviest rank.  Deterministic: every rank
+    generates the same global batch from the seed and keeps its share."""
+    from sparseeventid_b200 import synthetic
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
+    n = batch * world
+    arr = synthetic.larcv_batch_3d(n, seed=seed) if dataset == "dune3d" else synthetic.larcv_batch_2d(n, seed=seed)
+    counts = (arr[..., -1] != synthetic.PAD).sum(axis=(1, 2))
+    order = np.argsort(-counts, kind="stable")
+    mine = []
+    for j, e in enumerate(order):
+        r = j % (2 * world)
+        r = r if r < world else 2 * world - 1 - r
+        if r == rank:
+            mine.append(int(e))
+    mine = np.sort(np.asarray(mine))
+    sub = np.ascontiguousarray(arr[mine])
+    coords, feats, bs = larcvsparse_to_scnsparse_3d(sub) if dataset == "dune3d" else larcvsparse_to_scnsparse_2d(sub)
+    labels = {k: v[mine] for k, v in synthetic.make_labels(n, seed=seed).items()}
+    return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -193,6 +218,16 @@ def conv_algorithmic(rec, elem_bytes):
     return flops, by
 
 
+def kernel_source_hash():
+    """sha256 of the dominant kernel's sources: ties a committed ncu summary to the build it was captured on."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("conv_tc.cu", "tc_ptx.cuh", "common.cuh"):
+        with open(os.path.join(ROOT, "sparseeventid_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def run_ours(args, rank, world, local_rank):
     import sparseconvnet as scn
     from sparseeventid_b200 import _lib
@@ -205,12 +240,18 @@ def run_ours(args, rank, world, local_rank):
     scn.set_precision(args.precision)
     peaks = load_peaks()
     trainer = Trainer(scn, args.dataset, device=dev, seed=0)
+    n_params = sum(p.numel() for p in trainer.model.parameters())
     lib = _lib.lib()
 
     # ---- inputs: a pool of distinct host batches per rank (pinned), mirrored on the device
     pool = []
     for i in range(args.pool):
-        coords, feats, bs, labels = host_batch(args.batch, 1234 + 100000 * rank + 1000 * i, args.dataset)
+        if world > 1 and args.same_batches:          # diagnostic: every rank steps through the SAME batches (no straggler term)
+            coords, feats, bs, labels = host_batch(args.batch, 1234 + 1000 * i, args.dataset)
+        elif world > 1 and not args.no_balance:
+            coords, feats, bs, labels = balanced_host_batch(args.batch, world, rank, 1234 + 1000 * i, args.dataset)
+        else:
+            coords, feats, bs, labels = host_batch(args.batch, 1234 + 100000 * rank + 1000 * i, args.dataset)
         h = {"coords": torch.from_numpy(coords).pin_memory(), "feats": torch.from_numpy(feats).pin_memory(),
              "labels": {k: torch.from_numpy(v).pin_memory() for k, v in labels.items()}, "bs": bs}
         pool.append(h)
@@ -359,12 +400,15 @@ def run_ours(args, rank, world, local_rank):
             t = sum(r["ms"] for r in tc) * 1e-3
             peak = peaks["bf16_tflops_sustained"]
             traffic, traffic_note = None, None
-            prof_path = os.path.join(ROOT, "profiles", "r01b_conv_tc_ncu_summary.json")
+            prof_path = os.path.join(ROOT, "profiles", "r02_conv_tc_ncu_summary.json")
             if os.path.exists(prof_path):      # dram bytes of ONE ncu --set full capture of this kernel (committed)
                 pj = json.load(open(prof_path))
-                traffic = pj.get("traffic_bytes_per_launch")
-                traffic_note = ("dram read+write of the captured launch (317485 rows, 64->64, 27 offsets; its algorithmic "
-                                f"bytes: {pj.get('algorithmic_bytes_per_launch')}); `achieved` averages all 216 launches of a step")
+                if pj.get("kernel_source_sha256") == kernel_source_hash():
+                    traffic = pj.get("traffic_bytes_per_launch")
+                    traffic_note = (f"dram read+write of the captured launch ({pj.get('shape')}; its algorithmic bytes: "
+                                    f"{pj.get('algorithmic_bytes_per_launch')}); `achieved` averages all conv launches of a step")
+                else:                          # a capture of another build says nothing about this run
+                    traffic_note = "stale: csrc/conv_tc.cu changed since profiles/r02_conv_tc_ncu_summary.json was captured"
             roof = {"bound": "tensor", "kernel": "gather-GEMM conv fwd/dgrad (k_conv_tc, tcgen05)", "achieved": fl / t / 1e12,
                     "peak": peak, "unit": "TFLOP/s", "frac": fl / t / 1e12 / peak, "traffic": traffic,
                     "traffic_note": traffic_note,
@@ -373,6 +417,19 @@ def run_ours(args, rank, world, local_rank):
                     "achieved_algorithmic_gbs": by / t / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
                     "frac_of_hbm": by / t / 1e9 / peaks["hbm_gbs"], "peak_source": peaks["_source"],
                     "share_of_step": sum(r["ms"] for r in tc) / 2 / (ms / args.steps)}
+            # per layer shape (the 8 convolutions of a level share it): achieved TFLOP/s, its fraction of the tensor
+            # peak and of the launch's binding roof = max(flops / tensor peak, algorithmic bytes / HBM peak)
+            per = {}
+            for r in tc:
+                key = f"{r['kind']} K={r['K']} {r['n_in']}->{r['n_out']} rows={r['rows_out']}"
+                a = per.setdefault(key, {"launches": 0, "us": 0.0, "flops": 0.0, "bytes": 0.0})
+                fl_r, by_r = conv_algorithmic(r, eb)
+                a["launches"] += 1; a["us"] += r["ms"] * 1e3; a["flops"] += fl_r; a["bytes"] += by_r
+            roof["per_layer_shape"] = {
+                k: {"launches_per_step": v["launches"] / 2, "avg_us": round(v["us"] / v["launches"], 1),
+                    "tflops": round(v["flops"] / v["us"] / 1e6, 1), "frac_of_tensor_peak": round(v["flops"] / v["us"] / 1e6 / peak, 4),
+                    "frac_of_binding_roof": round(max(v["flops"] / (peak * 1e12), v["bytes"] / (peaks["hbm_gbs"] * 1e9)) / (v["us"] * 1e-6), 4)}
+                for k, v in sorted(per.items(), key=lambda kv: -kv[1]["us"])}
             try:
                 # per launch the binding roof is max(flops / tensor peak, algorithmic bytes / HBM peak): at these widths
                 # (arithmetic intensity below the 207 FLOP/B ridge) it is usually the HBM one
@@ -404,9 +461,12 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.dataset} default encoder (56 sparse convs, 20.9M params) + 4 heads, training "
-                                   f"step, batch {args.batch} events/GPU, precision mode {args.precision}",
+            "config": {"workload": f"{args.dataset} default encoder (56 sparse convs) + 4 heads, {n_params / 1e6:.2f}M params, "
+                                   f"training step, batch {args.batch} events/GPU, precision mode {args.precision}",
                        "events_per_gpu": args.batch, "mean_voxels_per_batch": n_voxels, "parallelism": f"dp{world}",
+                       "sharding": ("one rank" if world == 1 else "identical batches on every rank (diagnostic)" if args.same_batches
+                                    else "contiguous by event" if args.no_balance else
+                                    "by event, dealt in a snake over the voxel-count order (equal events and ~equal voxels per rank)"),
                        "l2_policy": "inputs_larger_than_L2 (activations of one step >> 126 MB; "
                                     f"{args.pool} distinct batches cycled)"},
             "clocks": clocks,
@@ -416,6 +476,8 @@ def run_ours(args, rank, world, local_rank):
                     "loss_first_last": [losses[0], losses[-1]] if losses else None,
                     "losses_finite": bool(np.all(np.isfinite(losses)))},
             "gpu_launches": launches,
+            "rulebook_ms": round(sum(v["ms_per_step"] for k, v in (breakdown or {}).items() if k.startswith("rulebook")), 3),
+            "rulebook_ms_note": "hash build + InputLayer rules + all submanifold / strided neighbour tables of one batch, GPU time on the rulebook stream (overlaps the feature kernels)",
             "roofline": roof,
             "cpu_baseline": cpu,
             "breakdown_ms_per_step": {k: round(v["ms_per_step"], 3) for k, v in (breakdown or {}).items()},
@@ -436,6 +498,8 @@ def main():
     ap.add_argument("--cpu-events", type=int, default=8, help="events per step of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="do not build the next batch's rulebooks ahead")
+    ap.add_argument("--no-balance", action="store_true", help="N>1: contiguous event sharding instead of voxel-count balancing")
+    ap.add_argument("--same-batches", action="store_true", help="N>1 diagnostic: identical batches on every rank")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -163,6 +163,12 @@ int scn_rulebook_pairs(const int32_t* nbr, int K, int64_t n, int64_t n_pad, int3
  * Output element type follows precision (fp32 or bf16); n_in/n_out below are B_k's own dims. */
 int scn_conv_prep_weights(const float* W, int K, int Cin, int Cout, int transpose, int mirror,
                           int precision, int feat_dtype, void* out, void* stream);
+/* Every weight image of a network in one launch (a trainer calls it once per step, then passes skip_prep = 1 to the
+ * module entry points below).  descs: DEVICE array of n x 8 int64 {W pointer, image pointer, K, Cin, Cout,
+ * transpose | mirror << 1, index of the image's first element in the concatenated index space, unused}; total =
+ * sum of K*Cin*Cout.  Only for images of the tcgen05 path (scn_conv_path == 2); an image whose n_in is not a multiple
+ * of 64 must have been zero-filled once (its unused half rows are never written). */
+int scn_conv_prep_weights_batched(const void* descs, int n, int64_t total, void* stream);
 /* Which kernel family runs a (K, n_in, n_out) contraction for features of feat_dtype:
  *   0 exact fp32 FMA (B_k fp32 [k][c][n]);  1 mma.sync tensor cores (B_k bf16 [k][n][c]);
  *   2 tcgen05 tensor cores + TMEM (B_k as pre-swizzled 128-byte-row bf16 tiles).

@@ -42,6 +42,7 @@ SIGNATURES = {
     "scn_rulebook_count": (_i, [_p, _i, _i64, _i64, _p, _p]),
     "scn_rulebook_pairs": (_i, [_p, _i, _i64, _i64, _p, _p, _p, _p, _sz, _p]),
     "scn_conv_prep_weights": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "scn_conv_prep_weights_batched": (_i, [_p, _i, _i64, _p]),
     "scn_conv_path": (_i, [_i, _i, _i, _i, _i]),
     "scn_conv_prep_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "scn_conv_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p]),

@@ -572,7 +572,48 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
   img[off] = __float2bfloat16_rn(v);
 }
 
+// All weight images of a network in ONE launch (the trainer calls it once per step instead of 112 per-module launches):
+// descs = n x 8 int64 {W, img, K, Cin, Cout, transpose | mirror << 1, first element index, unused}; element i of the
+// concatenated index space belongs to the descriptor d with first[d] <= i < first[d + 1].
+__global__ void k_prep_weights_tc_batched(const long long* __restrict__ descs, int n, long long total) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid * 8 + 6] <= i) lo = mid; else hi = mid - 1;
+  }
+  const long long* d = descs + lo * 8;
+  const float* W = reinterpret_cast<const float*>(d[0]);
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(d[1]);
+  const int K = (int)d[2], Cin = (int)d[3], Cout = (int)d[4], transpose = (int)(d[5] & 1), mirror = (int)((d[5] >> 1) & 1);
+  const long long li = i - d[6];
+  const int n_in = transpose ? Cout : Cin, n_out = transpose ? Cin : Cout;
+  const int nch = (n_in + KC - 1) / KC, pair = n_in == 32;
+  int k = (int)(li / ((long long)n_in * n_out));
+  int rem = (int)(li - (long long)k * n_in * n_out);
+  int nn = rem / n_in, c = rem % n_in;
+  int src_k = (transpose && mirror) ? K - 1 - k : k;
+  int ci = transpose ? nn : c, co = transpose ? c : nn;
+  float v = W[((long long)src_k * Cin + ci) * Cout + co];
+  const int q = pair ? (k >> 1) : k * nch + c / KC;
+  const int chunk = pair ? (k & 1) * 4 + (c >> 3) : (c % KC) >> 3;
+  size_t off = ((size_t)q * n_out + nn) * 64 + (size_t)((chunk ^ (nn & 7)) << 3) + (c & 7);
+  img[off] = __float2bfloat16_rn(v);
+}
+
 }  // namespace tc
+
+// descs: device array of n x 8 int64 (see k_prep_weights_tc_batched); images whose n_in is not a multiple of 64 must
+// have been zero-filled once by the caller (their unused half rows are never written).  tcgen05-path images only.
+extern "C" int scn_conv_prep_weights_batched(const void* descs, int n, int64_t total, void* stream) {
+  if (n <= 0 || total <= 0) return SCN_OK;
+  if (!descs) return SCN_ERR_ARG;
+  tc::k_prep_weights_tc_batched<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const long long*)descs, n,
+                                                                                       (long long)total);
+  SCN_LAUNCH_CHECK();
+  return SCN_OK;
+}
 
 // Debug: device buffer of 4 roles x 256 stages x 8 marks (uint64) filled by CTA 0 of the following launches; NULL disables.
 static unsigned long long* g_tc_dbg = nullptr;

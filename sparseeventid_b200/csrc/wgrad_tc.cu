@@ -18,6 +18,8 @@
 // Replaces SCN's dConvolution_KMxKN_backward_dW_A/B; reference call sites
 // src/networks/sparse_building_blocks.py:29-34,110-117 (backward).
 #include <cstdlib>
+#include <map>
+#include <mutex>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -26,8 +28,6 @@ namespace wg {
 
 using namespace tcptx;
 
-constexpr int PAIRS = 64;                 // pairs (MMA K rows) per stage
-constexpr int BLK_BYTES = PAIRS * 128;    // one 64-channel block of a stage: 64 rows x 128 B
 constexpr int EPI_WARPS = 4;              // warps 0..3 (TMEM lane quarter = warp index)
 constexpr int PROD_WARPS = 6;             // warps 4..9; the first NPW are active, two slots each
 constexpr int WARP_MMA = EPI_WARPS + PROD_WARPS;
@@ -39,7 +39,8 @@ struct Params {
   const __nv_bfloat16* x;       // [n_in_rows, Cin]
   const __nv_bfloat16* dout;    // [n_rows, Cout]
   const int32_t* nbr;           // [K][n_pad]: input row of output row o at offset k, or -1
-  float* dW;                    // [K][Cin][Cout], accumulated into
+  float* dW;                    // [K][Cin][Cout], accumulated into (by k_wgrad_reduce, or by atomics when part == nullptr)
+  float* part;                  // [gridDim.x][Cin][Cout] partial sums, one slab per CTA, or nullptr
   int64_t n_rows, n_pad;
   int K, Cin, Cout;
   int nca, ncb;                 // 64-channel blocks per stage: A (even: M = 128 reads two), B
@@ -74,11 +75,12 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 
 // NA / NB: 64-channel blocks of a stage's A (x rows) / B (dout rows) operand = ceil(Cin / 64), ceil(Cout / 64)
 // HALF: Cin == Cout == 32, rows are 64 bytes: 4 lanes per row and 8 rows per pass instead of 8 lanes / 4 rows
-// TEAM (wide layers, NA + NB >= 4: a stage is 32-48 KB and only 4-6 slots fit): producers work in TEAMS of two warps.
-// Both warps of a team walk the same blocks and build the same pair ring (private copies: no communication), and at
-// emit time warp 0 copies the x rows, warp 1 the dout rows of the stage; a producer unit below is a team.
-template <int NA, int NB, bool HALF, bool TEAM>
+// PAIRS: pairs (MMA K rows) per stage: 64, or 32 for the wide layers (NA + NB >= 5: a 64-pair stage is 40-48 KB, only 4
+// slots = 2 producer warps fit; measured 78 us for 258 k pairs at 160 channels against 73 us for 805 k pairs at 128).
+// (Two-warp producer teams per stage were measured too and are slower: 117 -> 168 us at 96 channels.)
+template <int NA, int NB, bool HALF, int PAIRS>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
+  constexpr int BLK_BYTES = PAIRS * 128;                 // one 64-channel block of a stage: PAIRS rows x 128 B
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
     if (lane == 0) {
       for (int s = 0; s < slots; ++s) {
         st_release_u32(seq + 4u * (uint32_t)s, 0u);
-        mbar_init(afull(s), TEAM ? 64 : 32);     // the lanes of the owning producer warp (team), each when its copies landed
+        mbar_init(afull(s), 32);                 // the 32 lanes of the owning producer warp, each when its copies landed
         mbar_init(aempty(s), 1);                 // one tcgen05.commit
       }
       for (int w = 0; w < PROD_WARPS; ++w) st_release_u32(done + 4u * (uint32_t)w, 0u);
@@ -132,11 +134,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // ================================ producers =============================================
-    const int wi = warp - EPI_WARPS;                        // producer warp
-    const int pw = TEAM ? (wi >> 1) : wi;                   // producer unit (warp or team): owns slots pw and pw + NPW
-    const int role = TEAM ? (wi & 1) : 0;                   // TEAM: 0 copies the x rows (A blocks), 1 the dout rows (B blocks)
+    const int pw = warp - EPI_WARPS;
     if (pw < NPW) {
-      int2* ring = rings + wi * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
+      int2* ring = rings + pw * RING;                       // .x: x row offset / 16 B, .y: dout row offset / 16 B
       const uint32_t xvec = (uint32_t)p.Cin >> 3, dvec = (uint32_t)p.Cout >> 3;
       const uint32_t lt = (1u << lane) - 1u;
       constexpr int LPR = HALF ? 4 : 8;                     // lanes per row
@@ -170,24 +170,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
           const uint32_t dst = (sbase + (uint32_t)row * 128u + ((uint32_t)(row & 7) << 4)) ^ csw;
           const unsigned char* xs = xsrc + ((uint64_t)(uint32_t)e.x << 4);
           const unsigned char* ds = dsrc + ((uint64_t)(uint32_t)e.y << 4);
-          if (!TEAM || role == 0) {
 #pragma unroll
-            for (int b = 0; b < NA; ++b) {                   // x row -> A blocks
-              const bool ok = live && a_ok[b];
-              cp_async16(dst + (uint32_t)b * BLK_BYTES, ok ? xs + b * 128 : xs, ok ? 16u : 0u);
-            }
+          for (int b = 0; b < NA; ++b) {                     // x row -> A blocks
+            const bool ok = live && a_ok[b];
+            cp_async16(dst + (uint32_t)b * BLK_BYTES, ok ? xs + b * 128 : xs, ok ? 16u : 0u);
           }
-          if (!TEAM || role == 1) {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {                   // dout row -> B blocks
-              const bool ok = live && b_ok[b];
-              cp_async16(dst + (uint32_t)(NA + b) * BLK_BYTES, ok ? ds + b * 128 : ds, ok ? 16u : 0u);
-            }
+          for (int b = 0; b < NB; ++b) {                     // dout row -> B blocks
+            const bool ok = live && b_ok[b];
+            cp_async16(dst + (uint32_t)(NA + b) * BLK_BYTES, ok ? ds + b * 128 : ds, ok ? 16u : 0u);
           }
         }
         cp_async_arrive_noinc(afull(slot));
         __syncwarp();
-        if (lane == 0 && role == 0)                          // (TEAM: the landing barrier still needs the other warp's 32 arrivals)
+        if (lane == 0)
           st_release_u32(seq + 4u * (uint32_t)slot, ((uint32_t)emitted + 1u) | ((((uint32_t)emitted >> 1) & 1u) << 31));
         head = (head + take) & (RING - 1);
         pending -= take;
@@ -223,7 +219,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
         while (pending >= PAIRS) emit(PAIRS);
       }
       if (pending > 0) emit(pending);
-      if (lane == 0 && role == 0) st_release_u32(done + 4u * (uint32_t)pw, (uint32_t)emitted + 1u);
+      if (lane == 0) st_release_u32(done + 4u * (uint32_t)pw, (uint32_t)emitted + 1u);
     }
   } else if (warp == WARP_MMA) {
     // ================================ MMA issuer ============================================
@@ -286,14 +282,26 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
     mbar_wait_sleep(accf, 0u);
     tc_fence_after();
     const uint32_t any = ld_acquire_u32(done + 4u * (uint32_t)PROD_WARPS);
-    if (any == 2u) {
-      for (int mb = 0; mb < (NA + 1) / 2; ++mb) {
-        const int cin = mb * 128 + warp * 32 + lane;                            // accumulator row == input channel
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * p.Cout);
-        for (int c0 = 0; c0 < p.Cout; c0 += 32) {
-          uint32_t v[32];
+    // The CTA's Cin x Cout partial sum goes to its own slab with plain 16-byte stores; k_wgrad_reduce then adds the slabs of
+    // an offset in a fixed order (deterministic).  Atomics straight into dW were ~44% of the kernel's time on the
+    // deep levels (148-296 CTAs x 25-37 k red.global.add each; ncu: the other warps idle at the exit barrier meanwhile).
+    for (int mb = 0; mb < (NA + 1) / 2; ++mb) {
+      const int cin = mb * 128 + warp * 32 + lane;                            // accumulator row == input channel
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mb * p.Cout);
+      for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+        uint32_t v[32];
+        if (any == 2u) {
           tmem_ld32(taddr + (uint32_t)c0, v);
-          if (cin < p.Cin) {
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;                             // no pair in this CTA's range: a slab of zeros
+        }
+        if (cin < p.Cin) {
+          if (p.part != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.part + ((size_t)blockIdx.x * p.Cin + cin) * p.Cout + c0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) dst[e] = make_uint4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          } else {
             float* dst = p.dW + ((int64_t)k * p.Cin + cin) * p.Cout + c0;
 #pragma unroll
             for (int e = 0; e < 32; ++e) {
@@ -313,6 +321,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
+}
+
+// dW[k] += sum over the CTAs of offset k of their slabs (4 floats per thread, slabs added in CTA order: deterministic)
+__global__ void k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dW, int K, int CC, int s_other, int s_centre,
+                               int centre) {
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  if (i >= (int64_t)K * CC) return;
+  const int k = (int)(i / CC);
+  const int e = (int)(i - (int64_t)k * CC);
+  int first, count;
+  if (centre < 0 || k < centre) { first = k * s_other; count = s_other; }
+  else if (k == centre) { first = centre * s_other; count = s_centre; }
+  else { first = centre * s_other + s_centre + (k - centre - 1) * s_other; count = s_other; }
+  // dW may be a view into a flat gradient arena: only 4-byte aligned, so it is read and written as scalars
+  float4 acc = make_float4(dW[i], dW[i + 1], dW[i + 2], dW[i + 3]);
+  for (int c = 0; c < count; ++c) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (size_t)(first + c) * CC + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  dW[i] = acc.x; dW[i + 1] = acc.y; dW[i + 2] = acc.z; dW[i + 3] = acc.w;
+}
+
+// library-owned slab buffer per (device, stream), grown on demand (a growth is a cudaFree + cudaMalloc, i.e. a device
+// synchronisation; it happens a handful of times in the first step).  nullptr if the allocation fails (atomics path).
+float* wgrad_slabs(size_t bytes, cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, std::pair<float*, size_t>> table;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  auto& e = table[{dev, s}];
+  if (e.second >= bytes) return e.first;
+  if (e.first != nullptr) {
+    if (cudaStreamSynchronize(s) != cudaSuccess) return nullptr;
+    cudaFree(e.first);
+    e = {nullptr, 0};
+  }
+  const size_t want = bytes + bytes / 4;
+  float* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+  e = {p, want};
+  return p;
 }
 
 }  // namespace wg
@@ -339,31 +389,29 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
   p.nca = (Cin + 63) / 64;
   p.ncb = (Cout + 63) / 64;
   if (p.nmb * Cout > 512) return SCN_ERR_UNSUPPORTED;
-  const uint32_t slot_bytes = (uint32_t)(p.nca + p.ncb) * wg::BLK_BYTES;
+  const int pairs = (p.nca + p.ncb) >= 5 ? 32 : 64;          // pairs per stage (see the kernel)
+  const uint32_t slot_bytes = (uint32_t)(p.nca + p.ncb) * (uint32_t)pairs * 128u;
   const uint32_t fixed = 1024u + 8u * (2 * wg::MAX_SLOTS + 2) + 16u + 4u * wg::MAX_SLOTS + 4u * wg::PROD_WARPS + 8u +
                          (uint32_t)wg::PROD_WARPS * wg::RING * 8u;
   int slots = (int)((226u * 1024u - fixed) / slot_bytes);
   if (slots > wg::MAX_SLOTS) slots = wg::MAX_SLOTS;
   slots &= ~1;
   if (slots < 2) return SCN_ERR_UNSUPPORTED;
-  const bool team = (p.nca + p.ncb) >= 4;
-  if (team && slots > wg::PROD_WARPS) slots = wg::PROD_WARPS & ~1;   // a team (two warps) per pair of slots
   p.slots = slots;
   p.npw = slots / 2;
-  // CTAs: two full waves (one CTA per SM at a time); the centre offset of an odd-sized (submanifold) table holds
-  // every row -> 3.5x the share.  Rounded DOWN so that the grid never spills into a third, nearly empty wave.
-  // Small tables get fewer CTAs: every CTA pays a fixed price (TMEM allocation, Cin*Cout atomics), so it should own
-  // ~1000 pairs or more (about 30% of the K*n table entries are pairs in the reference's networks).
-  int target = 2 * kNumSMs;
-  {
-    static const int pairs_per_cta = [] {                    // developer knob for sweeps: SCN_B200_WG_PAIRS=<pairs per CTA>
-      const char* e = std::getenv("SCN_B200_WG_PAIRS");
-      const int v = e ? std::atoi(e) : 0;
-      return v > 0 ? v : 1024;
-    }();
-    const int64_t by_work = (int64_t)((double)n_rows * K * 0.3 / (double)pairs_per_cta);
-    if (by_work < target) target = (int)(by_work < K ? K : by_work);
-  }
+  // CTAs (one per SM at a time: the kernel uses all of shared memory): ONE full wave, or two for big tables -- never
+  // a few CTAs more than a wave (150 CTAs on 148 SMs run for two waves: measured 86 us instead of ~45 at 20 k rows x
+  // 160 channels).  The centre offset of an odd-sized (submanifold) table holds every row -> 3.5x the share of the
+  // others.  Small tables get fewer CTAs: every CTA pays a fixed price (TMEM allocation, Cin*Cout atomics), so it
+  // should own ~500 pairs or more (about 30% of the K*n table entries are pairs in the reference's networks).
+  static const int pairs_per_cta = [] {                      // developer knob for sweeps: SCN_B200_WG_PAIRS=<pairs per CTA>
+    const char* e = std::getenv("SCN_B200_WG_PAIRS");
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : 512;
+  }();
+  const int64_t by_work = (int64_t)((double)n_rows * K * 0.3 / (double)pairs_per_cta);
+  int target = by_work >= (int64_t)(2 * kNumSMs * 0.85) ? 2 * kNumSMs : (by_work >= kNumSMs ? kNumSMs : (int)by_work);
+  if (target < K) target = K;
   const int64_t nblocks = (n_rows + 127) / 128;
   if ((K & 1) && K > 1) {
     p.centre = K / 2;
@@ -385,14 +433,24 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
   }
   const int grid = (p.centre >= 0 ? (K - 1) * p.s_other + p.s_centre : K * p.s_other);
   const size_t smem = (size_t)fixed + (size_t)slots * slot_bytes;
+  static const bool use_slabs = [] {                         // SCN_B200_WG_ATOMICS=1: the old epilogue (atomics into dW)
+    const char* e = std::getenv("SCN_B200_WG_ATOMICS");
+    return !(e && e[0] == '1');
+  }();
+  const int CC = Cin * Cout;
+  p.part = use_slabs ? wg::wgrad_slabs((size_t)grid * CC * sizeof(float), s) : nullptr;
   auto launch = [&](auto kern) -> int {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, wg::THREADS, smem, s>>>(p);
     SCN_LAUNCH_CHECK();
+    if (p.part != nullptr) {
+      wg::k_wgrad_reduce<<<grid_for((int64_t)K * CC / 4, 256), 256, 0, s>>>(p.part, dW, K, CC, p.s_other, p.s_centre, p.centre);
+      SCN_LAUNCH_CHECK();
+    }
     return SCN_OK;
   };
-  if (Cin == 32 && Cout == 32) return launch(wg::k_wgrad_tc<1, 1, true, false>);
-#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b, false, ((a) + (b) >= 4)>)
+  if (Cin == 32 && Cout == 32) return launch(wg::k_wgrad_tc<1, 1, true, 64>);
+#define WG_CASE(a, b) if (p.nca == a && p.ncb == b) return launch(wg::k_wgrad_tc<a, b, false, ((a) + (b) >= 5 ? 32 : 64)>)
   WG_CASE(1, 1); WG_CASE(1, 2); WG_CASE(1, 3); WG_CASE(1, 4);
   WG_CASE(2, 1); WG_CASE(2, 2); WG_CASE(2, 3); WG_CASE(2, 4);
   WG_CASE(3, 1); WG_CASE(3, 2); WG_CASE(3, 3); WG_CASE(3, 4);

@@ -72,6 +72,7 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
     ctx->saved_data["prec"] = prec;
     ctx->saved_data["direct_w"] = direct_w;
     ctx->saved_data["direct_b"] = direct_b;
+    ctx->saved_data["skip_prep"] = skip_prep;
     ctx->saved_data["wver"] = (int64_t)weight._version();
     return out;
   }
@@ -97,7 +98,7 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
                                    ctx->saved_data["n_out_rows"].toInt(), nbr_fwd.data_ptr<int32_t>(), nbr_fwd.size(1),
                                    nbr_bwd.data_ptr<int32_t>(), nbr_bwd.size(1), (int)K, (int)cin, (int)cout,
                                    weight.data_ptr<float>(), ctx->saved_data["mirror"].toBool() ? 1 : 0,
-                                   (int)ctx->saved_data["prec"].toInt(), optr(wimg_t), 0, optr(dx),
+                                   (int)ctx->saved_data["prec"].toInt(), optr(wimg_t), ctx->saved_data["skip_prep"].toBool() ? 1 : 0, optr(dx),
                                    wtarget->defined() ? wtarget->data_ptr<float>() : nullptr, gw.defined() ? 0 : 1,
                                    btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0, ws,
                                    cur_stream()),

@@ -34,20 +34,88 @@ def _grad_ready(param):
 
 class ConvWorkspace:
     """Per-module device workspaces of the convolution kernels: the buffers of the re-laid weight images (forward and
-    dgrad; rebuilt on every call, see modules._ConvBase._conv) and the kernel family chosen for this shape."""
+    dgrad) and the kernel family chosen for this shape.  The images are rebuilt on every call (modules._ConvBase._conv)
+    unless a trainer has prepared all of them for the current step in one launch (prepare_weight_images below)."""
 
-    __slots__ = ("fwd", "bwd", "fwd_key", "bwd_key", "path")
+    __slots__ = ("fwd", "bwd", "fwd_key", "bwd_key", "path", "prepared", "shape")
 
     def __init__(self, K, cin, cout, prec, dtype, device):
-        self.fwd = torch.empty((ops.conv_prep_bytes(K, cin, cout, prec, dtype),), dtype=torch.uint8, device=device)
+        self.fwd = torch.zeros((ops.conv_prep_bytes(K, cin, cout, prec, dtype),), dtype=torch.uint8, device=device)
         self.bwd = None
         self.fwd_key = self.bwd_key = None
         self.path = ops.conv_path(K, cin, cout, prec, dtype)
+        self.prepared = -1          # value of the global epoch for which both images are current
+        self.shape = (K, cin, cout, prec, dtype, device)
 
     def bwd_buffer(self, K, cin, cout, prec, dtype, device):
         if self.bwd is None:
-            self.bwd = torch.empty((ops.conv_prep_bytes(K, cout, cin, prec, dtype),), dtype=torch.uint8, device=device)
+            self.bwd = torch.zeros((ops.conv_prep_bytes(K, cout, cin, prec, dtype),), dtype=torch.uint8, device=device)
         return self.bwd
+
+
+# ---- all weight images of a model in one launch ------------------------------------------------------------------
+# A training step re-lays 56 forward and 56 dgrad weight images; per module that is 112 launches of a ~3 us kernel.
+# A trainer that knows when the parameters change (after optimizer.step()) has them all built at once:
+#     token = prepare_weight_images(modules)   # at the start of a step
+#     ... forward / backward (the modules pass skip_prep) ...
+#     release_weight_images()                  # before the optimizer updates the parameters
+_epoch = [0]
+_active = [False]
+
+
+def weight_images_current(ws) -> bool:
+    return _active[0] and ws.prepared == _epoch[0]
+
+
+def release_weight_images() -> None:
+    _active[0] = False
+
+
+class _ImagePlan:
+    __slots__ = ("descs", "n", "total", "workspaces", "key")
+
+
+_plans = {}
+
+
+def prepare_weight_images(modules) -> int:
+    """modules: the convolution modules of a model (objects with .weight, .mirror_dgrad and .workspace()).  Builds the
+    forward and dgrad images of every module on the tcgen05 path in ONE launch; the other paths keep their per-call
+    re-layout.  Returns the number of images built."""
+    from .. import _lib as L
+    mods = [m for m in modules if m.weight.is_cuda and m.weight.dtype == torch.float32 and m.weight.is_contiguous()]
+    if not mods:
+        return 0
+    prec, fdt = config.precision_code(), config.feature_dtype()
+    key = (id(mods[0]), len(mods), prec, fdt) + tuple(m.weight.data_ptr() for m in mods)
+    plan = _plans.get(key)
+    if plan is None:
+        rows, wss, first = [], [], 0
+        for m in mods:
+            w = m.weight
+            K, cin, cout = w.shape[0], w.shape[-2], w.shape[-1]
+            ws = m.workspace(K, cin, cout, prec, fdt, w.device)
+            if ws.path != 2 or ops.conv_path(K, cout, cin, prec, fdt) != 2:
+                continue
+            bwd = ws.bwd_buffer(K, cin, cout, prec, fdt, w.device)
+            rows.append([w.data_ptr(), ws.fwd.data_ptr(), K, cin, cout, 0, first, 0])
+            first += K * cin * cout
+            rows.append([w.data_ptr(), bwd.data_ptr(), K, cin, cout, 1 | (2 if m.mirror_dgrad else 0), first, 0])
+            first += K * cin * cout
+            wss.append(ws)
+        plan = _ImagePlan()
+        plan.n, plan.total, plan.workspaces = len(rows), first, wss
+        plan.descs = torch.tensor(rows, dtype=torch.int64, device=mods[0].weight.device) if rows else None
+        _plans.clear()              # one model at a time
+        _plans[key] = plan
+    _epoch[0] += 1
+    if plan.n:
+        L.check(L.lib().scn_conv_prep_weights_batched(plan.descs.data_ptr(), plan.n, plan.total, L.stream()),
+                "scn_conv_prep_weights_batched")
+        for ws in plan.workspaces:
+            ws.prepared = _epoch[0]
+    _active[0] = True
+    return plan.n
 
 
 class ConvFn(Function):
@@ -80,7 +148,8 @@ def _conv_forward(ctx, x, weight, bias, nbr_fwd, nbr_bwd, n_out_rows, mirror, ow
         if ws.path > 0 and x.dtype != fdt:
             x = ops.convert(x, fdt)
         # always re-laid: fused optimizers update parameters without bumping Tensor._version (see modules._conv)
-        out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd, False)
+        out = ops.conv_module_forward(x, weight, bias, nbr_fwd, n_out_rows, K, cin, cout, prec, fdt, ws.fwd,
+                                      weight_images_current(ws))
         ctx.ws = ws
     else:
         w3 = _w3(weight)
@@ -116,7 +185,7 @@ def _conv_backward(ctx, dout):
         wimg_t, skip = None, False
         if need_dx:
             wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
-            skip = False
+            skip = weight_images_current(ws)
         dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
                                       ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
                                       gw if gw is not None else dw, gw is None,

@@ -94,6 +94,8 @@ class OutputLayer(nn.Module):
 
 
 class _ConvBase(nn.Module):
+    mirror_dgrad = False         # dgrad weights: W[K-1-k]^T (submanifold) or W[k]^T (strided / deconvolution)
+
     def _init_params(self, nIn, nOut, bias):
         k = self.filter_volume
         w = torch.empty(k, 1, nIn, nOut)
@@ -132,8 +134,9 @@ class _ConvBase(nn.Module):
             if ws.path > 0 and x.dtype != fdt:
                 x = ops.convert(x, fdt)
             # The weight image is rebuilt on every call: there is no reliable "weights changed" signal (fused
-            # optimizers update parameters without bumping Tensor._version), and the re-layout is a ~4 us kernel.
-            skip = False
+            # optimizers update parameters without bumping Tensor._version), and the re-layout is a ~4 us kernel --
+            # unless a trainer has just built every image of the model in one launch (F.prepare_weight_images).
+            skip = F.weight_images_current(ws)
             wimg_t = None
             if x.requires_grad and torch.is_grad_enabled():
                 wimg_t = ws.bwd_buffer(K, cin, cout, prec, x.dtype, x.device)
@@ -150,6 +153,7 @@ class _ConvBase(nn.Module):
 class SubmanifoldConvolution(_ConvBase):
     """scn.SubmanifoldConvolution(dimension, nIn, nOut, filter_size, bias, groups=1)
     -- reference src/networks/sparse_building_blocks.py:29-34, src/networks/resnet.py:30-36,44-50,105-110."""
+    mirror_dgrad = True
 
     def __init__(self, dimension, nIn, nOut, filter_size, bias, groups=1):
         super().__init__()

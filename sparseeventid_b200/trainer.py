@@ -184,6 +184,7 @@ class Trainer:
     def __init__(self, scn, dataset: str = "dune3d", device="cuda", cfg: Optional[networks.EncoderConfig] = None,
                  seed: int = 0, weight_decay: float = 1e-6, peak_lr: float = 3e-3, fused_adam: Optional[bool] = None):
         torch.manual_seed(seed)
+        self.scn, self._convs = scn, None
         enc, head = networks.build_networks(scn, dataset, cfg)
         self.model = networks.EventIDModel(enc, head).to(device)
         self.device = torch.device(device)
@@ -235,11 +236,20 @@ class Trainer:
         """batch: (coords [N,4], features [N,1], batch_size) on self.device; labels: dict of int64 [B].
         prefetch: the next step's batch tuple (same tensor objects that will be passed then), optional."""
         self.arena.zero()
-        logits = self.model(batch)
-        loss = networks.focal_loss(labels, logits)
-        if prefetch is not None:
-            self.prefetch_rulebooks(prefetch, prefetch_ready)
-        loss.backward()
+        prep = getattr(self.scn, "prepare_weight_images", None)        # every conv weight image of the step in one launch
+        if prep is not None and self.device.type == "cuda":
+            if self._convs is None:
+                self._convs = [m for m in self.model.modules() if hasattr(m, "mirror_dgrad") and hasattr(m, "workspace")]
+            prep(self._convs)
+        try:
+            logits = self.model(batch)
+            loss = networks.focal_loss(labels, logits)
+            if prefetch is not None:
+                self.prefetch_rulebooks(prefetch, prefetch_ready)
+            loss.backward()
+        finally:
+            if prep is not None:
+                self.scn.release_weight_images()                       # the optimizer is about to change the parameters
         self.arena.finish()
         self.opt.step()
         self.sched.step()

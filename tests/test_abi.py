@@ -124,3 +124,19 @@ def test_torch_extension_builds_and_exports_the_module_functions():
     assert ext is not None
     for name in ("conv", "batch_norm", "add_leaky", "leaky", "set_grad_ready_callback"):
         assert hasattr(ext, name), name
+
+
+@pytest.mark.gpu
+def test_plain_c_caller_runs_on_the_gpu(tmp_path):
+    """tools/abi_harness.c -- a C99 program with no Python / torch in the process -- drives the hot path through
+    include/scn_b200.h on the device and checks its results itself (InputLayer rules, convolutions, pooling)."""
+    import subprocess
+    from sparseeventid_b200 import build
+    exe = tmp_path / "abi_harness"
+    subprocess.run(["gcc", "-std=c99", "-O2", "-I", os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tools", "abi_harness.c"), "-L", os.path.dirname(build.LIB), "-lscn_b200",
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-lm", "-o", str(exe)], check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.dirname(build.LIB) + ":/usr/local/cuda/lib64:" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([str(exe)], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "all checks passed" in r.stdout

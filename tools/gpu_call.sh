@@ -15,6 +15,11 @@ for s in "$@"; do
     sweepq) step "tc sweep quick" timeout 300 python tools/tc_sweep.py quick ;;
     bench) step "bench" bash -c 'timeout 400 python bench.py --no-cpu-baseline > gpurun_out/bench_n1.json && tail -c 2500 gpurun_out/bench_n1.json' ;;
     benchfull) step "bench full" bash -c 'timeout 600 python bench.py > gpurun_out/bench_n1.json && tail -c 2500 gpurun_out/bench_n1.json' ;;
+    wgsweep) step "wgrad kernel tests" timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k wgrad || exit 1
+        step "wgrad sweep (default)" timeout 200 python tools/wgrad_sweep.py ;;
+    ncu_wgrad) for i in 4 1; do
+        step "ncu k_wgrad_tc shape $i" bash -c "timeout 120 python tools/wgrad_sweep.py $i > gpurun_out/plain_wg$i.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wgrad_tc -s 3 -c 1 -f -o gpurun_out/wgrad_tc_shape$i python tools/wgrad_sweep.py $i > gpurun_out/ncu_wg$i.log 2>&1; tail -2 gpurun_out/ncu_wg$i.log"
+      done ;;
     ncu_conv) for a in "495518 27 32 32" "317485 27 64 64"; do
         tag=$(echo $a | tr ' ' '_')
         step "ncu k_conv_tc $a" bash -c "TC_PROFILE_CHECK=0 timeout 120 python tools/tc_profile.py $a 3 > gpurun_out/plain_$tag.log 2>&1 && TC_PROFILE_CHECK=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc -s 2 -c 1 -f -o gpurun_out/conv_tc_$tag python tools/tc_profile.py $a 3 > gpurun_out/ncu_$tag.log 2>&1; tail -3 gpurun_out/ncu_$tag.log"

@@ -13,7 +13,10 @@ dev = "cuda"
 SHAPES = [(495518, 27, 32, 32, 0.19), (317485, 27, 64, 64, 0.32), (154605, 27, 96, 96, 0.44), (59700, 27, 128, 128, 0.48),
           (20727, 27, 160, 160, 0.44), (7332, 27, 192, 192, 0.36), (317485, 8, 32, 64, 0.195), (154605, 8, 64, 96, 0.26),
           (20727, 8, 128, 160, 0.36), (7332, 8, 160, 192, 0.35), (7332, 1, 192, 128, 1.0)]
-for n, K, cin, cout, dens in SHAPES:
+only = int(sys.argv[1]) if len(sys.argv) > 1 else -1
+for si, (n, K, cin, cout, dens) in enumerate(SHAPES):
+    if only >= 0 and si != only:
+        continue
     torch.manual_seed(0)
     n_pad = ops.pad128(n)
     nbr = torch.full((K, n_pad), -1, dtype=torch.int32, device=dev)
