@@ -235,6 +235,15 @@ int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C
                     const float* gamma, const float* beta, const float* save_mean,
                     const float* save_invstd, int training, float leakiness, double* stats_ws,
                     void* dx, float* dgamma, float* dbeta, int accumulate_params, void* stream);
+/* scn_bn_backward that also writes dx_colsum[c] = sum over the n rows of dx[:, c] as stored (fp32 [C]; may be NULL):
+ * when the BatchNormalization follows a convolution with a bias (src/networks/sparse_building_blocks.py:29-39) that
+ * IS the convolution's bias gradient (SCN: Convolution backward, d_bias = column sums of d_output), produced in the
+ * pass that writes dx instead of by one more pass over it. */
+int scn_bn_backward_colsum(const void* x, const void* dout, int dtype, int64_t n, int C,
+                           const float* gamma, const float* beta, const float* save_mean,
+                           const float* save_invstd, int training, float leakiness, double* stats_ws,
+                           void* dx, float* dgamma, float* dbeta, int accumulate_params,
+                           float* dx_colsum, void* stream);
 
 int scn_leaky_forward(const void* x, int dtype, int64_t count, float leak, void* out, void* stream);
 int scn_leaky_backward(const void* x, const void* dout, int dtype, int64_t count, float leak,

@@ -54,6 +54,7 @@ SIGNATURES = {
                                       _p, _p, _i, _p, _i, _p, _p]),
     "scn_bn_forward": (_i, [_p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p]),
+    "scn_bn_backward_colsum": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p, _p]),
     "scn_leaky_forward": (_i, [_p, _i, _i64, _f, _p, _p]),
     "scn_leaky_backward": (_i, [_p, _p, _i, _i64, _f, _p, _p]),
     "scn_add_forward": (_i, [_p, _p, _i, _i64, _f, _p, _p]),

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 
 #include "common.cuh"
@@ -492,6 +493,364 @@ __global__ void __launch_bounds__(256) k_bn_bwd_fused(const T* __restrict__ x, c
     for (int i = threadIdx.x; i < 2 * C; i += 256) acc[i] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training-mode BatchNormalization as TWO ordinary launches per direction (default; C % 8 == 0, C <= 2048):
+//   statistics kernel: column sums -> fp64 accumulators (zero on entry); the LAST block to finish (atomic ticket) folds
+//                      them into per-channel fp32 coefficients (forward: scale / shift + saved and running statistics;
+//                      backward: the three coefficients of dx + dgamma / dbeta) and zeroes accumulators and ticket,
+//   apply kernel:      every thread loads the coefficients of its 8 channels and streams the rows.  The backward apply
+//                      also sums the columns of the dx it stores: that is the bias gradient of the convolution in front
+//                      of the BatchNorm (56 column-sum launches and one read of every dx per step otherwise).
+// Measured against the cooperative single-launch kernels above (ncu, 495 k rows x 32 channels, backward): 18% of the
+// kernel was its final grid barrier + re-zeroing, 7% the first barrier, 102 registers held it to 2 blocks per SM, a
+// cooperative launch costs ~6-10 us more than an ordinary one on the stream, and every thread folded the statistics of
+// its channels in fp64 (two divisions and a square root per channel: ~6 us per block on the thin fp64 pipe).  Here the
+// kernels run at 3-4 blocks x 256 threads per SM with 64 B in flight per thread and no fp64 outside one block.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Raw8;                       // 8 consecutive elements, kept packed while in flight
+template <> struct Raw8<__nv_bfloat16> {
+  uint4 u;
+  __device__ __forceinline__ void ld(const __nv_bfloat16* p) { u = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void get(float* o) const {
+    o[0] = __uint_as_float(u.x << 16); o[1] = __uint_as_float(u.x & 0xffff0000u);
+    o[2] = __uint_as_float(u.y << 16); o[3] = __uint_as_float(u.y & 0xffff0000u);
+    o[4] = __uint_as_float(u.z << 16); o[5] = __uint_as_float(u.z & 0xffff0000u);
+    o[6] = __uint_as_float(u.w << 16); o[7] = __uint_as_float(u.w & 0xffff0000u);
+  }
+};
+template <> struct Raw8<float> {
+  float4 a, b;
+  __device__ __forceinline__ void ld(const float* p) { a = ld4(p); b = ld4(p + 4); }
+  __device__ __forceinline__ void get(float* o) const {
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+  }
+};
+// store 8 values and add what was STORED (after rounding to T) to cs[8]
+__device__ __forceinline__ void store8_sum(__nv_bfloat16* p, const float* v, float* cs) {
+  Raw8<__nv_bfloat16> r;
+  r.u.x = pack_bf16x2(v[0], v[1]); r.u.y = pack_bf16x2(v[2], v[3]);
+  r.u.z = pack_bf16x2(v[4], v[5]); r.u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = r.u;
+  float f[8];
+  r.get(f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] += f[k];
+}
+__device__ __forceinline__ void store8_sum(float* p, const float* v, float* cs) {
+  LoadVec<float, 8>::st(p, v);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] += v[k];
+}
+
+// Per-thread partial sums a[8] (and b[8] when TWO) (thread = row slot ty x channel group tx) -> acc[c] += sum a,
+// acc[C + c] += sum b.  When the channel groups of a row divide a warp (C = 32, 64, 128, 256) lanes that own the same
+// channels are summed with shuffles first and only one partial per warp goes through shared memory; otherwise one
+// partial per row slot (RY <= 21 then).  sred: 256 x 16 floats.
+template <bool TWO>
+__device__ __forceinline__ void block_col_sums(float* a, float* b, int C, int CV, int RY, int tx, int ty, bool active,
+                                               float* sred, double* acc) {
+  constexpr int W = TWO ? 16 : 8;
+  int parts;
+  if ((32 % CV) == 0) {
+    for (int m = CV; m < 32; m <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[k] += __shfl_xor_sync(0xffffffffu, a[k], m);
+        if (TWO) b[k] += __shfl_xor_sync(0xffffffffu, b[k], m);
+      }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane < CV) {
+      float* dst = sred + ((size_t)w * CV + tx) * W;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { dst[k] = a[k]; if (TWO) dst[8 + k] = b[k]; }
+    }
+    parts = 8;
+  } else {
+    if (active) {
+      float* dst = sred + ((size_t)ty * CV + tx) * W;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { dst[k] = a[k]; if (TWO) dst[8 + k] = b[k]; }
+    }
+    parts = RY;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CV * W; i += 256) {
+    const int cx = i / W, w = i % W;
+    float sum = 0.f;
+    for (int y = 0; y < parts; ++y) sum += sred[((size_t)y * CV + cx) * W + w];
+    atomicAdd(acc + (size_t)(w >> 3) * C + cx * 8 + (w & 7), (double)sum);
+  }
+}
+
+// true in every thread of the LAST block of the grid to get here; that block then sees every block's atomics
+__device__ __forceinline__ bool last_block(unsigned* ticket) {
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) __threadfence();
+  return last;
+}
+
+// coef: fp32 [4][2048] per (device, stream): forward {scale, shift}, backward {scale, shift, e1, e2}
+constexpr int kCoefStride = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_bn_stats2(const T* __restrict__ x, int64_t n, int C, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* running_mean,
+                                                      float* running_var, float eps, float momentum,
+                                                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                      double* acc, unsigned* ticket, float* __restrict__ coef) {
+  __shared__ float sred[256 * 16];
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const bool active = ty < RY;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (active) {
+    float pv[8];
+    { Raw8<T> p; p.ld(x + tx * 8); p.get(pv); }          // pivot = row 0 (kills the cancellation in E[x^2] - E[x]^2)
+    const T* px = x + tx * 8;
+    int64_t r = (int64_t)blockIdx.x * RY + ty;
+    for (; r + 3 * stride < n; r += 4 * stride) {
+      Raw8<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].ld(px + (r + u * stride) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        v[u].get(f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float d = f[k] - pv[k]; a[k] += d; b[k] = fmaf(d, d, b[k]); }
+      }
+    }
+    for (; r < n; r += stride) {
+      Raw8<T> v;
+      v.ld(px + r * C);
+      float f[8];
+      v.get(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = f[k] - pv[k]; a[k] += d; b[k] = fmaf(d, d, b[k]); }
+    }
+  }
+  block_col_sums<true>(a, b, C, CV, RY, tx, ty, active, sred, acc);
+  if (!last_block(ticket)) return;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const double s1 = __ldcg(acc + c) / (double)n, s2 = __ldcg(acc + C + c) / (double)n;
+    const double mean = (double)Elem<T>::ld(x + c) + s1;
+    double var = s2 - s1 * s1;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean, is = (float)(1.0 / sqrt(var + (double)eps));
+    const double unbiased = var * (double)n / (double)(n > 1 ? n - 1 : 1);
+    running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
+    running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * unbiased);
+    save_mean[c] = m;
+    save_invstd[c] = is;
+    const float sc = is * (gamma ? gamma[c] : 1.f);
+    coef[c] = sc;
+    coef[kCoefStride + c] = (beta ? beta[c] : 0.f) - m * sc;
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 4) k_bn_apply2(const T* __restrict__ x, int64_t n, int C, float leak,
+                                                      const float* __restrict__ coef, T* __restrict__ out) {
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  if (ty >= RY) return;
+  float sc[8], sh[8];
+  {
+    const float4 s0 = ld4(coef + tx * 8), s1 = ld4(coef + tx * 8 + 4);
+    const float4 h0 = ld4(coef + kCoefStride + tx * 8), h1 = ld4(coef + kCoefStride + tx * 8 + 4);
+    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
+    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+  }
+  const T* px = x + tx * 8;
+  T* po = out + tx * 8;
+  int64_t r = (int64_t)blockIdx.x * RY + ty;
+  for (; r + 3 * stride < n; r += 4 * stride) {
+    Raw8<T> v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u].ld(px + (r + u * stride) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      v[u].get(f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = fmaf(f[k], sc[k], sh[k]);
+        f[k] = (leak != 1.f && !(y > 0.f)) ? y * leak : y;
+      }
+      LoadVec<T, 8>::st(po + (r + u * stride) * C, f);
+    }
+  }
+  for (; r < n; r += stride) {
+    Raw8<T> v;
+    v.ld(px + r * C);
+    float f[8];
+    v.get(f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float y = fmaf(f[k], sc[k], sh[k]);
+      f[k] = (leak != 1.f && !(y > 0.f)) ? y * leak : y;
+    }
+    LoadVec<T, 8>::st(po + r * C, f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 3) k_bn_bwd_stats2(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float leak, double* acc, unsigned* ticket, float* __restrict__ coef,
+                                                          float* dgamma, float* dbeta, int accumulate) {
+  __shared__ float sred[256 * 16];
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const bool active = ty < RY;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  float a[8], b[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = b[k] = 0.f;
+  if (active) {
+    // xhat = x * is + nm (nm = -mean * is); the fused leaky ReLU's mask is the sign of y = x * sc + sh, the very
+    // expression the forward evaluated (sc = is * gamma, sh = beta - mean * sc)
+    float is[8], nm[8], sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = tx * 8 + k;
+      is[k] = invstd[c];
+      nm[k] = -mean[c] * is[k];
+      sc[k] = is[k] * (gamma ? gamma[c] : 1.f);
+      sh[k] = (beta ? beta[c] : 0.f) - mean[c] * sc[k];
+    }
+    const T* px = x + tx * 8;
+    const T* pd = dout + tx * 8;
+    auto body = [&](const Raw8<T>& rv, const Raw8<T>& rd) {
+      float v[8], d[8];
+      rv.get(v);
+      rd.get(d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = fmaf(v[k], is[k], nm[k]);
+        const float y = fmaf(v[k], sc[k], sh[k]);
+        const float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+        a[k] += dd;
+        b[k] = fmaf(dd, xh, b[k]);
+      }
+    };
+    int64_t r = (int64_t)blockIdx.x * RY + ty;
+    for (; r + stride < n; r += 2 * stride) {
+      Raw8<T> v[2], d[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { v[u].ld(px + (r + u * stride) * C); d[u].ld(pd + (r + u * stride) * C); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) body(v[u], d[u]);
+    }
+    for (; r < n; r += stride) {
+      Raw8<T> v, d;
+      v.ld(px + r * C);
+      d.ld(pd + r * C);
+      body(v, d);
+    }
+  }
+  block_col_sums<true>(a, b, C, CV, RY, tx, ty, active, sred, acc);
+  if (!last_block(ticket)) return;
+  // dx = gamma * is * (d - s1 - xhat * s2), xhat = (x - mean) * is, folded into three coefficients per channel:
+  // dx = sc * d - (x * e2 + e1) with sc = gamma * is, e2 = sc * s2 * is, e1 = sc * (s1 - s2 * mean * is)
+  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const double sa = __ldcg(acc + c), sb = __ldcg(acc + C + c);
+    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sa;
+    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sb;
+    const float m = mean[c], is = invstd[c];
+    const float sc = is * (gamma ? gamma[c] : 1.f);
+    const float s1 = (float)sa * inv_n, s2 = (float)sb * inv_n;
+    coef[c] = sc;
+    coef[kCoefStride + c] = (beta ? beta[c] : 0.f) - m * sc;
+    coef[2 * kCoefStride + c] = sc * (s1 - s2 * m * is);
+    coef[3 * kCoefStride + c] = sc * s2 * is;
+    acc[c] = 0.0;
+    acc[C + c] = 0.0;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// COLSUM: also colsum[c] = sum over rows of the dx values as stored (acc: C zeroed doubles, left zero)
+template <typename T, bool COLSUM>
+__global__ void __launch_bounds__(256, 4) k_bn_bwd_apply2(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
+                                                          float leak, const float* __restrict__ coef, T* __restrict__ dx,
+                                                          double* acc, unsigned* ticket, float* __restrict__ colsum) {
+  __shared__ float sred[COLSUM ? 256 * 8 : 1];
+  const int CV = C >> 3, RY = 256 / CV;
+  const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
+  const bool active = ty < RY;
+  const int64_t stride = (int64_t)gridDim.x * RY;
+  float cs[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) cs[k] = 0.f;
+  if (active) {
+    // the mask of the fused leaky ReLU is the sign of y = x * sc + sh as in the forward
+    float sc[8], sh[8], e1[8], e2[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float4 q0 = ld4(coef + tx * 8 + 4 * h), q1 = ld4(coef + kCoefStride + tx * 8 + 4 * h);
+      const float4 q2 = ld4(coef + 2 * kCoefStride + tx * 8 + 4 * h), q3 = ld4(coef + 3 * kCoefStride + tx * 8 + 4 * h);
+      sc[4 * h] = q0.x; sc[4 * h + 1] = q0.y; sc[4 * h + 2] = q0.z; sc[4 * h + 3] = q0.w;
+      sh[4 * h] = q1.x; sh[4 * h + 1] = q1.y; sh[4 * h + 2] = q1.z; sh[4 * h + 3] = q1.w;
+      e1[4 * h] = q2.x; e1[4 * h + 1] = q2.y; e1[4 * h + 2] = q2.z; e1[4 * h + 3] = q2.w;
+      e2[4 * h] = q3.x; e2[4 * h + 1] = q3.y; e2[4 * h + 2] = q3.z; e2[4 * h + 3] = q3.w;
+    }
+    const T* px = x + tx * 8;
+    const T* pd = dout + tx * 8;
+    T* po = dx + tx * 8;
+    auto body = [&](const Raw8<T>& rv, const Raw8<T>& rd, T* dst) {
+      float v[8], d[8];
+      rv.get(v);
+      rd.get(d);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float y = fmaf(v[k], sc[k], sh[k]);
+        const float dd = (leak != 1.f && !(y > 0.f)) ? d[k] * leak : d[k];
+        v[k] = fmaf(dd, sc[k], -fmaf(v[k], e2[k], e1[k]));
+      }
+      if (COLSUM) store8_sum(dst, v, cs);
+      else LoadVec<T, 8>::st(dst, v);
+    };
+    int64_t r = (int64_t)blockIdx.x * RY + ty;
+    for (; r + stride < n; r += 2 * stride) {
+      Raw8<T> v[2], d[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { v[u].ld(px + (r + u * stride) * C); d[u].ld(pd + (r + u * stride) * C); }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) body(v[u], d[u], po + (r + u * stride) * C);
+    }
+    for (; r < n; r += stride) {
+      Raw8<T> v, d;
+      v.ld(px + r * C);
+      d.ld(pd + r * C);
+      body(v, d, po + r * C);
+    }
+  }
+  if (COLSUM) {
+    block_col_sums<false>(cs, nullptr, C, CV, RY, tx, ty, active, sred, acc);
+    if (!last_block(ticket)) return;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      colsum[c] = (float)__ldcg(acc + c);
+      acc[c] = 0.0;
+    }
+    if (threadIdx.x == 0) *ticket = 0u;
+  }
+}
+
 // Column sums (conv bias gradient) in ONE launch: blocks add their partial sums to the zeroed fp64 accumulators, the
 // last block to finish (atomic ticket) writes / accumulates the result and zeroes accumulators and ticket again.
 // acc: [2048] doubles (zero on entry and exit), ticket: the unsigned right behind them.
@@ -564,20 +923,29 @@ double* zero_scratch(cudaStream_t s) {
   auto it = table.find({dev, s});
   if (it != table.end()) return it->second;
   double* p = nullptr;
-  if (cudaMalloc(&p, (3 * 2048 + 2) * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
-  else if (cudaMemsetAsync(p, 0, (3 * 2048 + 2) * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
+  if (cudaMalloc(&p, (3 * 2048 + 2 + 2 * kCoefStride) * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+  else if (cudaMemsetAsync(p, 0, (3 * 2048 + 2 + 2 * kCoefStride) * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
   table[{dev, s}] = p;
   return p;
 }
 // (Channel-sliced kernels -- one block per 8 channels over all rows, no grid barrier -- were measured for the small levels
 // and are slower: 50 / 71 us against 36 / 24 us at 20 k rows x 160 channels: a warp then touches 32 different rows.)
-bool bn_fused_enabled() {
+// SCN_B200_BN_FUSED: 0 = four-launch reference path, 1 = cooperative single-launch kernels, 2 (default) = two launches
+int bn_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("SCN_B200_BN_FUSED");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
   }
-  return v == 1;
+  return v;
+}
+bool bn_fused_enabled() { return bn_mode() != 0; }
+// grid of the two-launch kernels: >= 4 rows per thread, at most one resident wave (per_sm blocks per SM)
+int bn_grid2(int64_t n, int ry, int per_sm) {
+  int64_t g = (n + (int64_t)ry * 4 - 1) / ((int64_t)ry * 4);
+  const int64_t cap = (int64_t)kNumSMs * per_sm;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
 }
 
 template <typename T, int VEC>
@@ -765,6 +1133,17 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)out) & 15) == 0;
   double* const ws_caller = ws;
   double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
+  if (zws != nullptr && bn_mode() == 2) {
+    const int ry = 256 / (C >> 3);
+    const int g = bn_grid2(n, ry, 4);
+    unsigned* ticket = reinterpret_cast<unsigned*>(zws + 3 * 2048 + 1);
+    float* coef = reinterpret_cast<float*>(zws + 3 * 2048 + 2);
+    k_bn_stats2<T><<<g, 256, 0, s>>>(x, n, C, gamma, beta, rm, rv, eps, momentum, save_mean, save_invstd, zws, ticket, coef);
+    SCN_LAUNCH_CHECK();
+    k_bn_apply2<T><<<g, 256, 0, s>>>(x, n, C, leak, coef, out);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   if (zws != nullptr) {
     ws = zws;                                 // library-owned accumulators, all zero between kernels
     const int ry = 256 / (C >> 3);
@@ -812,11 +1191,25 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
 template <typename T>
 int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamma, const float* beta,
                   const float* mean, const float* invstd, int training, float leak, double* ws, T* dx,
-                  float* dgamma, float* dbeta, int accumulate, cudaStream_t s) {
+                  float* dgamma, float* dbeta, int accumulate, float* colsum, cudaStream_t s) {
   const bool vec = (C % 4) == 0;
   const bool vec8 = (C % 8) == 0 && (((uintptr_t)x | (uintptr_t)dout | (uintptr_t)dx) & 15) == 0;
   double* const ws_caller = ws;
   double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
+  if (zws != nullptr && bn_mode() == 2) {
+    const int ry = 256 / (C >> 3);
+    unsigned* ticket = reinterpret_cast<unsigned*>(zws + 3 * 2048 + 1);
+    float* coef = reinterpret_cast<float*>(zws + 3 * 2048 + 2);
+    k_bn_bwd_stats2<T><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, zws, ticket, coef,
+                                                          dgamma, dbeta, accumulate);
+    SCN_LAUNCH_CHECK();
+    if (colsum)
+      k_bn_bwd_apply2<T, true><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, leak, coef, dx, zws, ticket, colsum);
+    else
+      k_bn_bwd_apply2<T, false><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, leak, coef, dx, zws, ticket, nullptr);
+    SCN_LAUNCH_CHECK();
+    return SCN_OK;
+  }
   if (zws != nullptr) {
     ws = zws;
     const int ry = 256 / (C >> 3);
@@ -827,6 +1220,7 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
                     (void*)&beta, (void*)&leak, (void*)&ws, (void*)&dx, (void*)&dgamma, (void*)&dbeta, (void*)&accumulate};
     if (cudaLaunchCooperativeKernel((void*)kern, dim3((unsigned)g), dim3(256), args, smem, s) == cudaSuccess) {
       SCN_LAUNCH_CHECK();
+      if (colsum) return scn_col_sum(dx, std::is_same<T, float>::value ? SCN_F32 : SCN_BF16, n, C, ws_caller, colsum, s);
       return SCN_OK;
     }
     (void)cudaGetLastError();
@@ -841,7 +1235,10 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
   }
   k_acc_to_float<<<grid_for(C, 128), 128, 0, s>>>(ws, C, dgamma, dbeta, accumulate);
   SCN_LAUNCH_CHECK();
-  if (n == 0) return SCN_OK;
+  if (n == 0) {
+    if (colsum) SCN_CUDA(cudaMemsetAsync(colsum, 0, (size_t)C * sizeof(float), s));
+    return SCN_OK;
+  }
   int64_t total = n * C;
   if (vec8 && C <= 2048) {
     const int ry = 256 / (C >> 3);
@@ -856,6 +1253,8 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
     k_bn_bwd_apply<T, 1><<<grid_for(total, 256), 256, 0, s>>>(x, dout, total, C, n, mean, invstd, gamma, beta, leak,
                                                               training, ws, dx);
   SCN_LAUNCH_CHECK();
+  if (colsum)      // paths without the fused column sums: one more pass over dx
+    return scn_col_sum(dx, std::is_same<T, float>::value ? SCN_F32 : SCN_BF16, n, C, ws_caller, colsum, s);
   return SCN_OK;
 }
 
@@ -909,19 +1308,28 @@ extern "C" int scn_bn_forward(const void* x, int dtype, int64_t n, int C, const 
   return SCN_OK;
 }
 
-extern "C" int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C, const float* gamma,
-                               const float* beta, const float* save_mean, const float* save_invstd, int training,
-                               float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta,
-                               int accumulate_params, void* stream) {
+extern "C" int scn_bn_backward_colsum(const void* x, const void* dout, int dtype, int64_t n, int C, const float* gamma,
+                                      const float* beta, const float* save_mean, const float* save_invstd, int training,
+                                      float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta,
+                                      int accumulate_params, float* dx_colsum, void* stream) {
   if (C < 1 || !save_mean || !save_invstd || !stats_ws) return SCN_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
   DISPATCH_T(dtype,
              return bn_backward_t<float>((const float*)x, (const float*)dout, n, C, gamma, beta, save_mean, save_invstd,
-                                         training, leakiness, stats_ws, (float*)dx, dgamma, dbeta, accumulate_params, s),
+                                         training, leakiness, stats_ws, (float*)dx, dgamma, dbeta, accumulate_params,
+                                         dx_colsum, s),
              return bn_backward_t<__nv_bfloat16>((const __nv_bfloat16*)x, (const __nv_bfloat16*)dout, n, C, gamma, beta,
                                                  save_mean, save_invstd, training, leakiness, stats_ws,
-                                                 (__nv_bfloat16*)dx, dgamma, dbeta, accumulate_params, s));
+                                                 (__nv_bfloat16*)dx, dgamma, dbeta, accumulate_params, dx_colsum, s));
   return SCN_OK;
+}
+
+extern "C" int scn_bn_backward(const void* x, const void* dout, int dtype, int64_t n, int C, const float* gamma,
+                               const float* beta, const float* save_mean, const float* save_invstd, int training,
+                               float leakiness, double* stats_ws, void* dx, float* dgamma, float* dbeta,
+                               int accumulate_params, void* stream) {
+  return scn_bn_backward_colsum(x, dout, dtype, n, C, gamma, beta, save_mean, save_invstd, training, leakiness, stats_ws,
+                                dx, dgamma, dbeta, accumulate_params, nullptr, stream);
 }
 
 extern "C" int scn_col_sum(const void* x, int dtype, int64_t n, int C, double* stats_ws, float* out, void* stream) {

@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
     __syncwarp();
   } else if (warp < EPI_WARPS) {
     // ================================ epilogue: TMEM -> dW atomics ============================
-    mbar_wait_sleep(accf, 0u);
+    mbar_wait_long(accf, 0u);
     tc_fence_after();
     const uint32_t any = ld_acquire_u32(done + 4u * (uint32_t)PROD_WARPS);
     // The CTA's Cin x Cout partial sum goes to its own slab with plain 16-byte stores; k_wgrad_reduce then adds the slabs of

@@ -54,6 +54,18 @@ void grad_ready(const at::Tensor& p) {
   if (!g_ready_cb->is_none()) (*g_ready_cb)(p);
 }
 
+// Column sums of the dx a BatchNorm backward just wrote (scn_bn_backward_colsum).  When that dx is the grad_output of a
+// convolution with a bias -- conv -> BatchNorm, every convolution of the reference's blocks
+// (src/networks/sparse_building_blocks.py:29-39) -- they ARE its bias gradient, and the convolution's backward skips its
+// own column-sum pass.  The dx tensor is kept alive with them, so a matching data pointer cannot be a recycled address.
+struct BnColsum {
+  at::Tensor dx, colsum;
+};
+BnColsum& last_bn_colsum() {
+  static BnColsum* v = new BnColsum();      // never destroyed: no CUDA free after the context is gone
+  return *v;
+}
+
 struct ConvFn : public torch::autograd::Function<ConvFn> {
   static at::Tensor forward(AutogradContext* ctx, at::Tensor x, at::Tensor weight, at::Tensor bias, at::Tensor nbr_fwd,
                             at::Tensor nbr_bwd, int64_t n_out_rows, bool mirror, int64_t prec, int64_t out_code,
@@ -92,7 +104,16 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
     if (need_db && !gb.defined()) db = at::empty(bias.sizes(), bias.options().dtype(at::kFloat));
     at::Tensor* wtarget = gw.defined() ? &gw : &dw;
     at::Tensor* btarget = gb.defined() ? &gb : &db;
-    double* ws = need_db ? stats_scratch(x.device(), cout).data_ptr<double>() : nullptr;
+    // bias gradient already summed by the BatchNorm backward that produced this grad_output?
+    BnColsum& bc = last_bn_colsum();
+    at::Tensor colsum;
+    if (need_db && bc.dx.defined() && bc.dx.data_ptr() == dout.data_ptr() && bc.dx.sizes() == dout.sizes() &&
+        bc.colsum.numel() == cout)
+      colsum = bc.colsum;
+    bc.dx = at::Tensor();
+    bc.colsum = at::Tensor();
+    const bool own_db = need_db && !colsum.defined();
+    double* ws = own_db ? stats_scratch(x.device(), cout).data_ptr<double>() : nullptr;
     TORCH_CHECK(!need_dx || has(wimg_t), "scn_b200: dgrad needs the transposed weight-image workspace");
     check(scn_conv_module_backward(x.data_ptr(), dcode(x), x.size(0), dout.data_ptr(), dcode(dout),
                                    ctx->saved_data["n_out_rows"].toInt(), nbr_fwd.data_ptr<int32_t>(), nbr_fwd.size(1),
@@ -100,9 +121,13 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
                                    weight.data_ptr<float>(), ctx->saved_data["mirror"].toBool() ? 1 : 0,
                                    (int)ctx->saved_data["prec"].toInt(), optr(wimg_t), ctx->saved_data["skip_prep"].toBool() ? 1 : 0, optr(dx),
                                    wtarget->defined() ? wtarget->data_ptr<float>() : nullptr, gw.defined() ? 0 : 1,
-                                   btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0, ws,
+                                   own_db && btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0, ws,
                                    cur_stream()),
           "scn_conv_module_backward");
+    if (colsum.defined()) {
+      if (gb.defined()) gb.add_(colsum.view_as(gb));
+      else db = colsum.view_as(bias);
+    }
     if (gw.defined()) grad_ready(weight);
     if (gb.defined()) grad_ready(bias);
     return {dx, dw, db, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(),
@@ -147,13 +172,19 @@ struct BatchNormFn : public torch::autograd::Function<BatchNormFn> {
     }
     at::Tensor dx = at::empty_like(x);
     float* sp = stats.data_ptr<float>();
-    check(scn_bn_backward(x.data_ptr(), dout.data_ptr(), dcode(x), n, (int)c,
-                          affine ? weight.data_ptr<float>() : nullptr, affine ? bias.data_ptr<float>() : nullptr, sp,
-                          sp + c, ctx->saved_data["training"].toBool() ? 1 : 0, (float)ctx->saved_data["leak"].toDouble(),
-                          stats_scratch(x.device(), c).data_ptr<double>(), dx.data_ptr(),
-                          acc ? gw.data_ptr<float>() : dg.data_ptr<float>(), acc ? gb.data_ptr<float>() : db.data_ptr<float>(),
-                          acc ? 1 : 0, cur_stream()),
-          "scn_bn_backward");
+    const bool training = ctx->saved_data["training"].toBool();
+    // training mode: the column sums of dx come out of the same pass (the bias gradient of a convolution in front)
+    at::Tensor colsum = (training && n > 0) ? at::empty({c}, x.options().dtype(at::kFloat)) : at::Tensor();
+    check(scn_bn_backward_colsum(x.data_ptr(), dout.data_ptr(), dcode(x), n, (int)c,
+                                 affine ? weight.data_ptr<float>() : nullptr, affine ? bias.data_ptr<float>() : nullptr, sp,
+                                 sp + c, training ? 1 : 0, (float)ctx->saved_data["leak"].toDouble(),
+                                 stats_scratch(x.device(), c).data_ptr<double>(), dx.data_ptr(),
+                                 acc ? gw.data_ptr<float>() : dg.data_ptr<float>(), acc ? gb.data_ptr<float>() : db.data_ptr<float>(),
+                                 acc ? 1 : 0, colsum.defined() ? colsum.data_ptr<float>() : nullptr, cur_stream()),
+          "scn_bn_backward_colsum");
+    BnColsum& bc = last_bn_colsum();
+    bc.dx = colsum.defined() ? dx : at::Tensor();
+    bc.colsum = colsum;
     if (acc) {
       grad_ready(weight);
       grad_ready(bias);

@@ -186,10 +186,22 @@ def _conv_backward(ctx, dout):
         if need_dx:
             wimg_t = ws.bwd_buffer(K, cin, cout, ctx.prec, xw.dtype, x.device)
             skip = weight_images_current(ws)
+        # bias gradient already summed by the BatchNorm backward that produced this grad_output?
+        bdx, colsum = _last_bn_colsum
+        _last_bn_colsum[:] = [None, None]
+        if not (need_db and bdx is not None and bdx.data_ptr() == dout.data_ptr() and bdx.shape == dout.shape
+                and colsum.numel() == cout):
+            colsum = None
+        own_db = need_db and colsum is None
         dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
                                       ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
                                       gw if gw is not None else dw, gw is None,
-                                      gb if gb is not None else db, gb is not None)
+                                      (gb if gb is not None else db) if own_db else None, gb is not None)
+        if colsum is not None:
+            if gb is not None:
+                gb.add_(colsum.view_as(gb))
+            else:
+                db = colsum.view_as(bias)
         if dx is not None and dx.dtype != x.dtype:
             dx = ops.convert(dx, x.dtype)
         if gw is not None:
@@ -208,6 +220,10 @@ def _conv_backward(ctx, dout):
     if need_db:
         db = ops.col_sum(dout)
     return dx, dw, db
+
+
+# [dx, column sums of dx] of the latest training-mode BatchNorm backward (dx kept alive: its address cannot be recycled)
+_last_bn_colsum = [None, None]
 
 
 class BatchNormFn(Function):
@@ -232,7 +248,13 @@ class BatchNormFn(Function):
             gw, gb = _direct_grad(ctx.params[0]), _direct_grad(ctx.params[1])
             if gw is None or gb is None:
                 gw = gb = None
-        dx, dg, db = ops.bn_backward(x, dout.contiguous(), g, b, stats, ctx.training, ctx.leak, gw, gb)
+        if ctx.training and x.shape[0] > 0:
+            # the column sums of dx come out of the same pass: the bias gradient of a convolution in front (_conv_backward)
+            dx, dg, db, colsum = ops.bn_backward(x, dout.contiguous(), g, b, stats, ctx.training, ctx.leak, gw, gb, True)
+            _last_bn_colsum[:] = [dx, colsum]
+        else:
+            dx, dg, db = ops.bn_backward(x, dout.contiguous(), g, b, stats, ctx.training, ctx.leak, gw, gb)
+            _last_bn_colsum[:] = [None, None]
         if gw is not None:
             _grad_ready(ctx.params[0])
             _grad_ready(ctx.params[1])

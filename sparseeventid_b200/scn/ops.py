@@ -319,8 +319,9 @@ def bn_forward(x, gamma, beta, rm, rv, training, eps, momentum, leak):
     return out, stats
 
 
-def bn_backward(x, dout, gamma, beta, stats, training, leak, dgamma=None, dbeta=None):
-    """-> (dx, dgamma, dbeta).  When dgamma/dbeta buffers are given the parameter gradients are ACCUMULATED into them."""
+def bn_backward(x, dout, gamma, beta, stats, training, leak, dgamma=None, dbeta=None, want_colsum=False):
+    """-> (dx, dgamma, dbeta) or, with want_colsum, (dx, dgamma, dbeta, column sums of dx [C] fp32).  When dgamma/dbeta
+    buffers are given the parameter gradients are ACCUMULATED into them."""
     n, c = x.shape
     dev = x.device
     ws = stats_scratch(dev, c)
@@ -329,15 +330,18 @@ def bn_backward(x, dout, gamma, beta, stats, training, leak, dgamma=None, dbeta=
     if not accumulate:
         both = torch.empty((2, c), dtype=torch.float32, device=dev)
         dgamma, dbeta = both[0], both[1]
+    colsum = torch.empty((c,), dtype=torch.float32, device=dev) if want_colsum else None
     p = _profiler
     e0 = p.begin() if p else None
     sp = stats.data_ptr()
-    L.check(L.lib().scn_bn_backward(x.data_ptr(), dout.data_ptr(), _DT[x.dtype], n, c, L.ptr(gamma), L.ptr(beta),
-                                    sp, sp + 4 * c, int(training), leak, ws.data_ptr(), dx.data_ptr(),
-                                    dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate), L.stream()),
-            "scn_bn_backward")
+    L.check(L.lib().scn_bn_backward_colsum(x.data_ptr(), dout.data_ptr(), _DT[x.dtype], n, c, L.ptr(gamma), L.ptr(beta),
+                                           sp, sp + 4 * c, int(training), leak, ws.data_ptr(), dx.data_ptr(),
+                                           dgamma.data_ptr(), dbeta.data_ptr(), int(accumulate), L.ptr(colsum), L.stream()),
+            "scn_bn_backward_colsum")
     if p:   # reduce pass reads x,dout; apply pass reads x,dout and writes dx
         p.end(e0, kind="bn_bwd", bytes=5.0 * x.numel() * x.element_size())
+    if want_colsum:
+        return dx, dgamma, dbeta, colsum
     return dx, dgamma, dbeta
 
 

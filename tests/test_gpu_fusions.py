@@ -1,0 +1,106 @@
+"""GPU tests of the fused / batched forms that sit between the per-layer kernels and the training step:
+
+  * scn_bn_backward_colsum: the column sums of dx produced by the BatchNorm backward's apply pass equal the sums of the
+    dx it stored (they replace the bias-gradient pass of the convolution in front of the BatchNorm, SCN's Convolution
+    backward as reached from src/networks/sparse_building_blocks.py:29-39),
+  * conv -> BatchNorm: the bias gradient the convolution ends up with equals the column sums of its grad_output,
+  * scn_conv_prep_weights_batched: every weight image built by the one-launch form is byte-identical to the image the
+    per-module call builds (forward and dgrad images, every channel configuration of the default network).
+"""
+import pytest
+import torch
+
+from helpers import blob_sites
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scn():
+    import sparseconvnet as s
+    return s
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("n,c", [(1, 32), (64, 192), (777, 96), (3000, 160), (5000, 32), (20000, 64), (9000, 128)])
+def test_bn_backward_colsum_is_the_sum_of_the_stored_dx(scn, n, c, dtype):
+    from sparseeventid_b200.scn import ops
+    g = torch.Generator(device="cuda").manual_seed(n + c)
+    x = (torch.randn(n, c, device="cuda", generator=g) * 2 + 0.5).to(dtype)
+    d = torch.randn(n, c, device="cuda", generator=g).to(dtype)
+    gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+    beta = torch.randn(c, device="cuda", generator=g) * 0.1
+    rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+    out, stats = ops.bn_forward(x, gamma, beta, rm, rv, True, 1e-4, 0.9, 0.333)
+    dx, dg, db, colsum = ops.bn_backward(x, d, gamma, beta, stats, True, 0.333, want_colsum=True)
+    dx2, dg2, db2 = ops.bn_backward(x, d, gamma, beta, stats, True, 0.333)
+    assert torch.equal(dx, dx2) and torch.allclose(dg, dg2, rtol=1e-5, atol=1e-5) and torch.allclose(db, db2, rtol=1e-5, atol=1e-5)
+    want = dx.double().sum(0)
+    scale = float(dx.double().abs().sum(0).max()) + 1e-12
+    assert float((colsum.double() - want).abs().max()) <= 2e-6 * scale + 1e-7, (n, c, dtype)
+    # and dx itself against the textbook formula in float64
+    xd, dd = x.double(), d.double()
+    mean, var = xd.mean(0), xd.var(0, unbiased=False)
+    xh = (xd - mean) / torch.sqrt(var + 1e-4)
+    y = xh * gamma.double() + beta.double()
+    dl = torch.where(y > 0, dd, dd * 0.333)
+    ref = gamma.double() / torch.sqrt(var + 1e-4) * (dl - dl.mean(0) - xh * (dl * xh).mean(0))
+    err = float((dx.double() - ref).norm() / (ref.norm() + 1e-30))
+    if n > 1:
+        assert err <= (5e-3 if dtype == torch.bfloat16 else 2e-5), (n, c, dtype, err)
+
+
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_conv_bias_gradient_through_batchnorm(scn, mode):
+    scn.set_precision(mode)
+    try:
+        torch.manual_seed(4)
+        c = 32
+        conv = scn.SubmanifoldConvolution(3, c, c, 3, True).cuda()
+        bn = scn.BatchNormLeakyReLU(c).cuda()
+        tail = scn.SubmanifoldConvolution(3, c, c, 3, True).cuda()
+        coords = torch.as_tensor(blob_sites(400, (20, 20, 20), 3, seed=21)).cuda()
+        feats = torch.randn(coords.shape[0], c).cuda()
+        x = scn.InputLayer(3, [20, 20, 20])((coords, feats, 3))
+        y = conv(x)
+        kept = []
+        y.features.register_hook(lambda gr: kept.append(gr.detach().clone()))
+        z = tail(bn(y))
+        z.features.float().square().sum().backward()
+        dout = kept[0].double()
+        want = dout.sum(0)
+        scale = float(dout.abs().sum(0).max()) + 1e-12
+        assert float((conv.bias.grad.double() - want).abs().max()) <= 2e-6 * scale + 1e-7
+        # the tail convolution's grad_output does not come from a BatchNorm: its own column-sum pass
+        assert conv.bias.grad.shape == tail.bias.grad.shape and float(tail.bias.grad.abs().max()) > 0
+    finally:
+        scn.set_precision("fp32")
+
+
+def test_batched_weight_images_equal_per_module_images(scn):
+    from sparseeventid_b200 import _lib as L
+    from sparseeventid_b200.scn import config, functional as F, ops
+    scn.set_precision("bf16")
+    try:
+        torch.manual_seed(7)
+        mods = [scn.SubmanifoldConvolution(3, 32, 32, 3, True), scn.SubmanifoldConvolution(3, 64, 64, 3, False),
+                scn.SubmanifoldConvolution(3, 96, 96, 3, True), scn.SubmanifoldConvolution(3, 160, 160, 3, True),
+                scn.SubmanifoldConvolution(3, 192, 128, 1, True), scn.Convolution(3, 32, 64, 2, 2, False),
+                scn.Convolution(3, 64, 96, 2, 2, True), scn.Deconvolution(3, 128, 96, 2, 2, False),
+                scn.Convolution(3, 160, 192, 2, 2, False)]
+        mods = [m.cuda() for m in mods]
+        built = F.prepare_weight_images(mods)
+        assert built == 2 * len(mods)
+        prec, fdt = config.precision_code(), config.feature_dtype()
+        for m in mods:
+            w = m.weight
+            K, cin, cout = w.shape[0], w.shape[-2], w.shape[-1]
+            ws = m.workspace(K, cin, cout, prec, fdt, w.device)
+            w3 = w.detach().reshape(K, cin, cout).contiguous()
+            fwd = ops.prep_weights(w3, False, False, prec, fdt)
+            bwd = ops.prep_weights(w3, True, m.mirror_dgrad, prec, fdt)
+            assert torch.equal(ws.fwd[: fwd.numel()], fwd), (type(m).__name__, cin, cout, "forward image")
+            assert torch.equal(ws.bwd[: bwd.numel()], bwd), (type(m).__name__, cin, cout, "dgrad image")
+        F.release_weight_images()
+    finally:
+        scn.set_precision("fp32")
