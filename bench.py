@@ -182,20 +182,49 @@ def cpu_events_per_s(dataset, events, steps, warmup, seed=1234):
     return events / sec, sec, cores
 
 
+def workload_config(dataset, batch, n_params, n_voxels, world, sharding, pool):
+    """The `config` of BOTH arms (ours and --impl reference): the workload, not how an arm runs it (that is `dtype`,
+    `cpu_baseline.sample`, ...)."""
+    return {"workload": f"{dataset} default encoder (56 sparse convs) + 4 heads, {n_params / 1e6:.2f}M params, "
+                        f"training step, batch {batch} events/GPU",
+            "events_per_gpu": batch, "mean_voxels_per_batch": n_voxels, "parallelism": f"dp{world}",
+            "sharding": sharding,
+            "l2_policy": f"inputs_larger_than_L2 (activations of one step >> 126 MB; {pool} distinct batches cycled)"}
+
+
+def sharding_text(args, world):
+    if world == 1:
+        return "one rank"
+    if args.same_batches:
+        return "identical batches on every rank (diagnostic)"
+    if args.no_balance:
+        return "contiguous by event"
+    return "by event, dealt in a snake over the voxel-count order (equal events and ~equal voxels per rank)"
+
+
 def run_reference(args, rank):
+    """The CPU arm: the oracle port of SparseConvNet's CPU algorithm (SCN itself is absent from the image: kind
+    "port") on the host cores, on OUR arm's config; each step is a bounded sample of that workload (--cpu-events events
+    of the batch) so that the run ends within minutes."""
     if rank != 0:
         return
+    from oracle import sparseconvnet_oracle as oscn
+    from sparseeventid_b200 import networks
     events = args.cpu_events
+    world = args.gpus
+    enc, head = networks.build_networks(oscn, args.dataset)
+    n_params = sum(p.numel() for p in enc.parameters()) + sum(p.numel() for p in head.parameters())
+    del enc, head
+    n_voxels = int(np.mean([host_batch(args.batch, 1234 + 1000 * i, args.dataset)[0].shape[0] for i in range(args.pool)]))
     v, sec, cores = cpu_events_per_s(args.dataset, events, args.steps, min(args.warmup, 1))
-    sample = (f"{events} synthetic {args.dataset} events per step (bounded sample of the batch-{args.batch} workload), "
-              f"{args.steps} timed steps after {min(args.warmup, 1)} warm-up, fp32")
+    sample = (f"{events} of the {args.batch} synthetic {args.dataset} events of a batch per step (bounded sample), "
+              f"{args.steps} timed steps after {min(args.warmup, 1)} warm-up, fp32, the same training step "
+              f"(encoder + heads + focal loss + Adam) through the oracle port of SparseConvNet's CPU algorithm")
     line = {
         "impl": "reference", "metric": METRIC if args.dataset == "dune3d" else METRIC_2D, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.dataset} default encoder+heads training step, CPU, {events} events/step",
-                   "note": "SparseConvNet itself is absent from the image; this is the oracle port of its CPU "
-                           "algorithm (kind=port)"},
+        "config": workload_config(args.dataset, args.batch, n_params, n_voxels, world, sharding_text(args, world), args.pool),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -368,6 +397,23 @@ def run_ours(args, rank, world, local_rank):
     value = args.batch * world * args.steps / (ms * 1e-3)
     e2e = args.batch * world * args.steps / (ms_e2e * 1e-3)
 
+    # host time to ENQUEUE one step (stepping thread, GPU queue empty at the start so nothing throttles the host; the
+    # rulebooks of the step were prefetched by the step before, as in the timed loops): the step is host-bound when
+    # this approaches ms_per_step
+    import time as _time
+    step_resident(args.steps)                             # seeds the prefetch chain for the measured steps
+    host_ms = []
+    for i in range(3):
+        tr_thread = getattr(trainer, "_join_prefetch", None)
+        if tr_thread is not None:
+            tr_thread()
+        torch.cuda.synchronize()
+        t0 = _time.perf_counter()
+        step_resident(args.steps + 1 + i)
+        host_ms.append((_time.perf_counter() - t0) * 1e3)
+    torch.cuda.synchronize()
+    host_enqueue_ms = float(np.median(host_ms))
+
     # ---- instrumented pass (rank 0): CUDA events around every launch of this library's hot kernels
     # (every rank runs the two extra steps -- they contain the gradient all-reduce -- only rank 0 records)
     roof, breakdown = None, None
@@ -461,14 +507,8 @@ def run_ours(args, rank, world, local_rank):
             "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision != "fp32" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.dataset} default encoder (56 sparse convs) + 4 heads, {n_params / 1e6:.2f}M params, "
-                                   f"training step, batch {args.batch} events/GPU, precision mode {args.precision}",
-                       "events_per_gpu": args.batch, "mean_voxels_per_batch": n_voxels, "parallelism": f"dp{world}",
-                       "sharding": ("one rank" if world == 1 else "identical batches on every rank (diagnostic)" if args.same_batches
-                                    else "contiguous by event" if args.no_balance else
-                                    "by event, dealt in a snake over the voxel-count order (equal events and ~equal voxels per rank)"),
-                       "l2_policy": "inputs_larger_than_L2 (activations of one step >> 126 MB; "
-                                    f"{args.pool} distinct batches cycled)"},
+            "config": workload_config(args.dataset, args.batch, n_params, n_voxels, world, sharding_text(args, world), args.pool),
+            "precision_mode": args.precision,
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4,
@@ -476,6 +516,7 @@ def run_ours(args, rank, world, local_rank):
                     "loss_first_last": [losses[0], losses[-1]] if losses else None,
                     "losses_finite": bool(np.all(np.isfinite(losses)))},
             "gpu_launches": launches,
+            "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
             "rulebook_ms": round(sum(v["ms_per_step"] for k, v in (breakdown or {}).items() if k.startswith("rulebook")), 3),
             "rulebook_ms_note": "hash build + InputLayer rules + all submanifold / strided neighbour tables of one batch, GPU time on the rulebook stream (overlaps the feature kernels)",
             "roofline": roof,

@@ -62,9 +62,12 @@ def test_oracle_mirror_reproduces_legacy_fixture(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode,tol", [("fp32", TOL), ("bf16", 1e-1)])
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
 @pytest.mark.parametrize("case", sorted(LEGACY_CASES))
-def test_gpu_legacy_network_matches_fixture(case, mode, tol):
+def test_gpu_legacy_network_matches_fixture(case, mode):
+    """fp32 mode: within 2e-3 of the fixture (truth).  bf16 mode: no further from truth than 1.5x the distance of the
+    ORACLE run under the same stated precision (+ a floor of 2e-3; 1e-2 for the worst gradient norm): the bar a wrong
+    kernel fails and a kernel that merely rounds differently passes (see tests/test_golden_network.py)."""
     import sparseconvnet as scn
     want = np.load(os.path.join(GOLDEN, case + ".npz"))
     scn.set_precision(mode)
@@ -72,6 +75,18 @@ def test_gpu_legacy_network_matches_fixture(case, mode, tol):
         model, logits, loss = run(scn, case, "cuda")
         errs = errors(model, logits, loss, want)
         print(case, mode, {k: f"{v:.2e}" for k, v in errs.items()})
-        assert max(errs.values()) <= tol, errs
+        if mode == "fp32":
+            assert max(errs.values()) <= TOL, errs
+        else:
+            oscn.set_numerics(mode)
+            try:
+                o_model, o_logits, o_loss = run(oscn, case, "cpu")
+                o_errs = errors(o_model, o_logits, o_loss, want)
+            finally:
+                oscn.set_numerics("fp32")
+            print(case, "oracle[" + mode + "]", {k: f"{v:.2e}" for k, v in o_errs.items()})
+            for k, e in errs.items():
+                floor = 1e-2 if k == "grad_norms" else 2e-3
+                assert e <= 1.5 * o_errs[k] + floor, (k, e, o_errs[k])
     finally:
         scn.set_precision("bf16")
