@@ -216,6 +216,14 @@ int scn_conv_module_backward(const void* x, int x_dtype, int64_t n_in_rows, cons
                              int Cin, int Cout, const float* W, int mirror, int precision,
                              void* wimg_t, int skip_prep, void* dx, float* dW, int zero_dW,
                              float* dbias, int accumulate_dbias, double* stats_ws, void* stream);
+/* scn_conv_module_backward when the column sums of dout are already known (dout_colsum: fp32 [Cout], e.g. from
+ * scn_bn_backward_colsum; NULL = compute them): dbias (+)= dout_colsum without another pass over dout. */
+int scn_conv_module_backward_colsum(const void* x, int x_dtype, int64_t n_in_rows, const void* dout,
+                             int dout_dtype, int64_t n_out_rows, const int32_t* nbr_fwd,
+                             int64_t n_pad_fwd, const int32_t* nbr_bwd, int64_t n_pad_bwd, int K,
+                             int Cin, int Cout, const float* W, int mirror, int precision,
+                             void* wimg_t, int skip_prep, void* dx, float* dW, int zero_dW,
+                             float* dbias, int accumulate_dbias, const float* dout_colsum, double* stats_ws, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Bandwidth-bound layers.  Feature matrices are [n, C] row-major of `dtype`.

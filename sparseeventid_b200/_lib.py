@@ -52,6 +52,8 @@ SIGNATURES = {
     "scn_conv_module_forward": (_i, [_p, _i, _i64, _p, _i, _i64, _i64, _i, _i, _p, _p, _i, _p, _i, _p, _i, _p]),
     "scn_conv_module_backward": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p, _i, _i, _p, _i,
                                       _p, _p, _i, _p, _i, _p, _p]),
+    "scn_conv_module_backward_colsum": (_i, [_p, _i, _i64, _p, _i, _i64, _p, _i64, _p, _i64, _i, _i, _i, _p, _i, _i, _p, _i,
+                                      _p, _p, _i, _p, _i, _p, _p, _p]),
     "scn_bn_forward": (_i, [_p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _f, _f, _p, _p, _p, _p, _p]),
     "scn_bn_backward": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p]),
     "scn_bn_backward_colsum": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p, _p, _i, _f, _p, _p, _p, _p, _i, _p, _p]),

@@ -495,17 +495,19 @@ __global__ void __launch_bounds__(256) k_bn_bwd_fused(const T* __restrict__ x, c
 
 // ---------------------------------------------------------------------------------------------
 // Training-mode BatchNormalization as TWO ordinary launches per direction (default; C % 8 == 0, C <= 2048):
-//   statistics kernel: column sums -> fp64 accumulators (zero on entry); the LAST block to finish (atomic ticket) folds
-//                      them into per-channel fp32 coefficients (forward: scale / shift + saved and running statistics;
-//                      backward: the three coefficients of dx + dgamma / dbeta) and zeroes accumulators and ticket,
-//   apply kernel:      every thread loads the coefficients of its 8 channels and streams the rows.  The backward apply
-//                      also sums the columns of the dx it stores: that is the bias gradient of the convolution in front
-//                      of the BatchNorm (56 column-sum launches and one read of every dx per step otherwise).
+//   statistics kernel: column sums -> one of two sets of fp64 accumulators (zero on entry), nothing else,
+//   apply kernel:      every thread folds the statistics of its 8 channels into registers (forward: scale / shift,
+//                      block 0 also writes the saved and running statistics; backward: the three coefficients of dx,
+//                      block 0 writes dgamma / dbeta), zeroes the OTHER set of accumulators for the next call and
+//                      streams the rows.  The backward apply also sums the columns of the dx it stores: that is the
+//                      bias gradient of the convolution in front of the BatchNorm (56 column-sum launches and one read
+//                      of every dx per step otherwise).
 // Measured against the cooperative single-launch kernels above (ncu, 495 k rows x 32 channels, backward): 18% of the
 // kernel was its final grid barrier + re-zeroing, 7% the first barrier, 102 registers held it to 2 blocks per SM, a
 // cooperative launch costs ~6-10 us more than an ordinary one on the stream, and every thread folded the statistics of
-// its channels in fp64 (two divisions and a square root per channel: ~6 us per block on the thin fp64 pipe).  Here the
-// kernels run at 3-4 blocks x 256 threads per SM with 64 B in flight per thread and no fp64 outside one block.
+// its channels with fp64 divisions and square roots (~6 us per block on the thin fp64 pipe).  Here the kernels run at
+// 3-4 blocks x 256 threads per SM with 64 B in flight per thread; the fold is 2 fp64 multiplies, one fma and a
+// Newton-refined rsqrt per channel.
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct Raw8;                       // 8 consecutive elements, kept packed while in flight
 template <> struct Raw8<__nv_bfloat16> {
@@ -594,15 +596,19 @@ __device__ __forceinline__ bool last_block(unsigned* ticket) {
   return last;
 }
 
-// coef: fp32 [4][2048] per (device, stream): forward {scale, shift}, backward {scale, shift, e1, e2}
-constexpr int kCoefStride = 2048;
+// Two sets of accumulators, used alternately (BN call i of a stream uses set i & 1): the apply kernel of call i zeroes
+// the OTHER set -- nobody reads or writes it while that kernel runs -- so the statistics kernel needs no "last block
+// zeroes / finalises" tail (threadfence + ticket + a serial block: ~3 us of a ~8 us kernel on the deep levels) and the
+// statistics are folded per thread in the apply kernel: two fp64 multiplies, one fp64 fma and a Newton-refined
+// rsqrt per channel (no fp64 division or square root: those made the per-thread fold ~6 us per block).
+__device__ __forceinline__ float inv_sqrt_refined(double v) {
+  const float r = rsqrtf((float)v);
+  const double rd = (double)r;
+  return (float)(rd * (1.5 - 0.5 * v * rd * rd));       // one Newton step in fp64: correct to fp32 rounding
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256, 4) k_bn_stats2(const T* __restrict__ x, int64_t n, int C, const float* __restrict__ gamma,
-                                                      const float* __restrict__ beta, float* running_mean,
-                                                      float* running_var, float eps, float momentum,
-                                                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
-                                                      double* acc, unsigned* ticket, float* __restrict__ coef) {
+__global__ void __launch_bounds__(256, 4) k_bn_stats2(const T* __restrict__ x, int64_t n, int C, double* acc) {
   __shared__ float sred[256 * 16];
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
@@ -638,40 +644,42 @@ __global__ void __launch_bounds__(256, 4) k_bn_stats2(const T* __restrict__ x, i
     }
   }
   block_col_sums<true>(a, b, C, CV, RY, tx, ty, active, sred, acc);
-  if (!last_block(ticket)) return;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const double s1 = __ldcg(acc + c) / (double)n, s2 = __ldcg(acc + C + c) / (double)n;
-    const double mean = (double)Elem<T>::ld(x + c) + s1;
-    double var = s2 - s1 * s1;
-    if (var < 0.0) var = 0.0;
-    const float m = (float)mean, is = (float)(1.0 / sqrt(var + (double)eps));
-    const double unbiased = var * (double)n / (double)(n > 1 ? n - 1 : 1);
-    running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
-    running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * unbiased);
-    save_mean[c] = m;
-    save_invstd[c] = is;
-    const float sc = is * (gamma ? gamma[c] : 1.f);
-    coef[c] = sc;
-    coef[kCoefStride + c] = (beta ? beta[c] : 0.f) - m * sc;
-    acc[c] = 0.0;
-    acc[C + c] = 0.0;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256, 4) k_bn_apply2(const T* __restrict__ x, int64_t n, int C, float leak,
-                                                      const float* __restrict__ coef, T* __restrict__ out) {
+__global__ void __launch_bounds__(256, 4) k_bn_apply2(const T* __restrict__ x, int64_t n, int C, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, float* running_mean,
+                                                      float* running_var, float eps, float momentum, float leak,
+                                                      float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                                      const double* __restrict__ acc, double* __restrict__ acc_other,
+                                                      int zero_n, double inv_n, T* __restrict__ out) {
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const int64_t stride = (int64_t)gridDim.x * RY;
+  if (blockIdx.x == 0)                                   // the other set of accumulators: zero for the next BN call
+    for (int i = threadIdx.x; i < zero_n; i += 256) acc_other[i] = 0.0;
   if (ty >= RY) return;
-  float sc[8], sh[8];
-  {
-    const float4 s0 = ld4(coef + tx * 8), s1 = ld4(coef + tx * 8 + 4);
-    const float4 h0 = ld4(coef + kCoefStride + tx * 8), h1 = ld4(coef + kCoefStride + tx * 8 + 4);
-    sc[0] = s0.x; sc[1] = s0.y; sc[2] = s0.z; sc[3] = s0.w; sc[4] = s1.x; sc[5] = s1.y; sc[6] = s1.z; sc[7] = s1.w;
-    sh[0] = h0.x; sh[1] = h0.y; sh[2] = h0.z; sh[3] = h0.w; sh[4] = h1.x; sh[5] = h1.y; sh[6] = h1.z; sh[7] = h1.w;
+  float sc[8], sh[8], pv[8];
+  { Raw8<T> p; p.ld(x + tx * 8); p.get(pv); }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = tx * 8 + k;
+    // plain (L1-cached) loads: every thread of the grid reads these 2 C doubles; through L2 alone (ld.cg) the few
+    // cache lines they live in serialise the whole grid (measured: +15 us at 495 k rows)
+    const double s1 = acc[c] * inv_n, s2 = acc[C + c] * inv_n;
+    const double mean = (double)pv[k] + s1;
+    double var = fma(-s1, s1, s2);
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean, is = inv_sqrt_refined(var + (double)eps);
+    if (blockIdx.x == 0 && ty == 0) {
+      const double unbiased = var * (double)n / (double)(n > 1 ? n - 1 : 1);
+      running_mean[c] = (float)((double)momentum * running_mean[c] + (1.0 - (double)momentum) * mean);
+      running_var[c] = (float)((double)momentum * running_var[c] + (1.0 - (double)momentum) * unbiased);
+      save_mean[c] = m;
+      save_invstd[c] = is;
+    }
+    sc[k] = is * (gamma ? gamma[c] : 1.f);
+    sh[k] = (beta ? beta[c] : 0.f) - m * sc[k];
   }
   const T* px = x + tx * 8;
   T* po = out + tx * 8;
@@ -710,8 +718,7 @@ template <typename T>
 __global__ void __launch_bounds__(256, 3) k_bn_bwd_stats2(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                          float leak, double* acc, unsigned* ticket, float* __restrict__ coef,
-                                                          float* dgamma, float* dbeta, int accumulate) {
+                                                          float leak, double* acc) {
   __shared__ float sred[256 * 16];
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
@@ -763,51 +770,48 @@ __global__ void __launch_bounds__(256, 3) k_bn_bwd_stats2(const T* __restrict__ 
     }
   }
   block_col_sums<true>(a, b, C, CV, RY, tx, ty, active, sred, acc);
-  if (!last_block(ticket)) return;
-  // dx = gamma * is * (d - s1 - xhat * s2), xhat = (x - mean) * is, folded into three coefficients per channel:
-  // dx = sc * d - (x * e2 + e1) with sc = gamma * is, e2 = sc * s2 * is, e1 = sc * (s1 - s2 * mean * is)
-  const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const double sa = __ldcg(acc + c), sb = __ldcg(acc + C + c);
-    if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sa;
-    if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sb;
-    const float m = mean[c], is = invstd[c];
-    const float sc = is * (gamma ? gamma[c] : 1.f);
-    const float s1 = (float)sa * inv_n, s2 = (float)sb * inv_n;
-    coef[c] = sc;
-    coef[kCoefStride + c] = (beta ? beta[c] : 0.f) - m * sc;
-    coef[2 * kCoefStride + c] = sc * (s1 - s2 * m * is);
-    coef[3 * kCoefStride + c] = sc * s2 * is;
-    acc[c] = 0.0;
-    acc[C + c] = 0.0;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
 }
 
-// COLSUM: also colsum[c] = sum over rows of the dx values as stored (acc: C zeroed doubles, left zero)
+// COLSUM: also colsum[c] = sum over rows of the dx values as stored (colacc: C zeroed doubles, left zero)
 template <typename T, bool COLSUM>
-__global__ void __launch_bounds__(256, 4) k_bn_bwd_apply2(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
-                                                          float leak, const float* __restrict__ coef, T* __restrict__ dx,
-                                                          double* acc, unsigned* ticket, float* __restrict__ colsum) {
+__global__ void __launch_bounds__(256, COLSUM ? 3 : 4) k_bn_bwd_apply2(const T* __restrict__ x, const T* __restrict__ dout, int64_t n, int C,
+                                                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float leak, const double* __restrict__ acc,
+                                                          double* __restrict__ acc_other, int zero_n, T* __restrict__ dx,
+                                                          float* dgamma,
+                                                          float* dbeta, int accumulate, double* colacc, unsigned* ticket,
+                                                          float* __restrict__ colsum) {
   __shared__ float sred[COLSUM ? 256 * 8 : 1];
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const bool active = ty < RY;
   const int64_t stride = (int64_t)gridDim.x * RY;
+  if (blockIdx.x == 0)                                   // the other set of accumulators: zero for the next BN call
+    for (int i = threadIdx.x; i < zero_n; i += 256) acc_other[i] = 0.0;
   float cs[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) cs[k] = 0.f;
   if (active) {
-    // the mask of the fused leaky ReLU is the sign of y = x * sc + sh as in the forward
+    // dx = gamma * is * (d - s1 - xhat * s2), xhat = (x - mean) * is, folded into three coefficients per channel:
+    // dx = sc * d - (x * e2 + e1) with sc = gamma * is, e2 = sc * s2 * is, e1 = sc * (s1 - s2 * mean * is); the mask of
+    // the fused leaky ReLU is the sign of y = x * sc + sh as in the forward
     float sc[8], sh[8], e1[8], e2[8];
+    const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float4 q0 = ld4(coef + tx * 8 + 4 * h), q1 = ld4(coef + kCoefStride + tx * 8 + 4 * h);
-      const float4 q2 = ld4(coef + 2 * kCoefStride + tx * 8 + 4 * h), q3 = ld4(coef + 3 * kCoefStride + tx * 8 + 4 * h);
-      sc[4 * h] = q0.x; sc[4 * h + 1] = q0.y; sc[4 * h + 2] = q0.z; sc[4 * h + 3] = q0.w;
-      sh[4 * h] = q1.x; sh[4 * h + 1] = q1.y; sh[4 * h + 2] = q1.z; sh[4 * h + 3] = q1.w;
-      e1[4 * h] = q2.x; e1[4 * h + 1] = q2.y; e1[4 * h + 2] = q2.z; e1[4 * h + 3] = q2.w;
-      e2[4 * h] = q3.x; e2[4 * h + 1] = q3.y; e2[4 * h + 2] = q3.z; e2[4 * h + 3] = q3.w;
+    for (int k = 0; k < 8; ++k) {
+      const int c = tx * 8 + k;
+      const double sa = acc[c], sb = acc[C + c];          // L1-cached on purpose (see k_bn_apply2)
+      if (blockIdx.x == 0 && ty == 0) {
+        if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)sa;
+        if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)sb;
+      }
+      const float m = mean[c], is = invstd[c];
+      sc[k] = is * (gamma ? gamma[c] : 1.f);
+      sh[k] = (beta ? beta[c] : 0.f) - m * sc[k];
+      const float s1 = (float)sa * inv_n, s2 = (float)sb * inv_n;
+      e1[k] = sc[k] * (s1 - s2 * m * is);
+      e2[k] = sc[k] * s2 * is;
     }
     const T* px = x + tx * 8;
     const T* pd = dout + tx * 8;
@@ -841,11 +845,11 @@ __global__ void __launch_bounds__(256, 4) k_bn_bwd_apply2(const T* __restrict__ 
     }
   }
   if (COLSUM) {
-    block_col_sums<false>(cs, nullptr, C, CV, RY, tx, ty, active, sred, acc);
+    block_col_sums<false>(cs, nullptr, C, CV, RY, tx, ty, active, sred, colacc);
     if (!last_block(ticket)) return;
     for (int c = threadIdx.x; c < C; c += 256) {
-      colsum[c] = (float)__ldcg(acc + c);
-      acc[c] = 0.0;
+      colsum[c] = (float)__ldcg(colacc + c);
+      colacc[c] = 0.0;
     }
     if (threadIdx.x == 0) *ticket = 0u;
   }
@@ -914,19 +918,37 @@ int bn_coop_grid(K kern, int64_t n, int ry, size_t smem) {
 // (device, stream), allocated and zeroed once; every
 // fused kernel finds them zero and leaves them zero, so no memset precedes a launch.  nullptr if allocation fails
 // (the caller then takes the four-launch path).
+constexpr int kAcc1 = 3 * 2048 + 2;          // second set of BatchNorm accumulators (2 x 2048 doubles) behind the tickets
+constexpr size_t kScratchDoubles = (size_t)kAcc1 + 2 * 2048;
+struct ScratchEntry { double* p = nullptr; unsigned phase = 0; bool tried = false; int last_c[2] = {0, 0}; };
+static std::mutex g_scratch_mu;
+static std::map<std::pair<int, cudaStream_t>, ScratchEntry> g_scratch;
 double* zero_scratch(cudaStream_t s) {
-  static std::mutex mu;
-  static std::map<std::pair<int, cudaStream_t>, double*> table;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = table.find({dev, s});
-  if (it != table.end()) return it->second;
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  ScratchEntry& e = g_scratch[{dev, s}];
+  if (e.tried) return e.p;
+  e.tried = true;
   double* p = nullptr;
-  if (cudaMalloc(&p, (3 * 2048 + 2 + 2 * kCoefStride) * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
-  else if (cudaMemsetAsync(p, 0, (3 * 2048 + 2 + 2 * kCoefStride) * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
-  table[{dev, s}] = p;
+  if (cudaMalloc(&p, kScratchDoubles * sizeof(double)) != cudaSuccess) { (void)cudaGetLastError(); p = nullptr; }
+  else if (cudaMemsetAsync(p, 0, kScratchDoubles * sizeof(double), s) != cudaSuccess) { cudaFree(p); p = nullptr; }
+  e.p = p;
   return p;
+}
+// which set of BatchNorm accumulators the next two-launch BatchNorm call of this stream uses (alternates per call)
+// *zero_n: how many doubles of the OTHER set this call's apply kernel must clear -- what that set's last user (the
+// previous call, possibly with more channels than this one) accumulated into
+unsigned bn_next_phase(cudaStream_t s, int C, int* zero_n) {
+  int dev = 0;
+  (void)cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_scratch_mu);
+  ScratchEntry& e = g_scratch[{dev, s}];
+  const unsigned ph = e.phase & 1u;
+  e.phase ^= 1u;
+  *zero_n = 2 * e.last_c[ph ^ 1u];
+  e.last_c[ph] = C;
+  return ph;
 }
 // (Channel-sliced kernels -- one block per 8 channels over all rows, no grid barrier -- were measured for the small levels
 // and are slower: 50 / 71 us against 36 / 24 us at 20 k rows x 160 channels: a warp then touches 32 different rows.)
@@ -1136,11 +1158,14 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
   if (zws != nullptr && bn_mode() == 2) {
     const int ry = 256 / (C >> 3);
     const int g = bn_grid2(n, ry, 4);
-    unsigned* ticket = reinterpret_cast<unsigned*>(zws + 3 * 2048 + 1);
-    float* coef = reinterpret_cast<float*>(zws + 3 * 2048 + 2);
-    k_bn_stats2<T><<<g, 256, 0, s>>>(x, n, C, gamma, beta, rm, rv, eps, momentum, save_mean, save_invstd, zws, ticket, coef);
+    int zero_n = 0;
+    const unsigned ph = bn_next_phase(s, C, &zero_n);
+    double* acc = zws + (ph ? kAcc1 : 0);
+    double* other = zws + (ph ? 0 : kAcc1);
+    k_bn_stats2<T><<<g, 256, 0, s>>>(x, n, C, acc);
     SCN_LAUNCH_CHECK();
-    k_bn_apply2<T><<<g, 256, 0, s>>>(x, n, C, leak, coef, out);
+    k_bn_apply2<T><<<g, 256, 0, s>>>(x, n, C, gamma, beta, rm, rv, eps, momentum, leak, save_mean, save_invstd, acc, other,
+                                     zero_n, 1.0 / (double)n, out);
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }
@@ -1198,15 +1223,20 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
   double* zws = (training && vec8 && C <= 2048 && n > 0 && bn_fused_enabled()) ? zero_scratch(s) : nullptr;
   if (zws != nullptr && bn_mode() == 2) {
     const int ry = 256 / (C >> 3);
+    int zero_n = 0;
+    const unsigned ph = bn_next_phase(s, C, &zero_n);
+    double* acc = zws + (ph ? kAcc1 : 0);
+    double* other = zws + (ph ? 0 : kAcc1);
+    double* colacc = zws + 2 * 2048;                                   // shared with k_col_sum_fused (stream-ordered)
     unsigned* ticket = reinterpret_cast<unsigned*>(zws + 3 * 2048 + 1);
-    float* coef = reinterpret_cast<float*>(zws + 3 * 2048 + 2);
-    k_bn_bwd_stats2<T><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, zws, ticket, coef,
-                                                          dgamma, dbeta, accumulate);
+    k_bn_bwd_stats2<T><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc);
     SCN_LAUNCH_CHECK();
     if (colsum)
-      k_bn_bwd_apply2<T, true><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, leak, coef, dx, zws, ticket, colsum);
+      k_bn_bwd_apply2<T, true><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc, other,
+                                                                  zero_n, dx, dgamma, dbeta, accumulate, colacc, ticket, colsum);
     else
-      k_bn_bwd_apply2<T, false><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, leak, coef, dx, zws, ticket, nullptr);
+      k_bn_bwd_apply2<T, false><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc, other,
+                                                                   zero_n, dx, dgamma, dbeta, accumulate, colacc, ticket, nullptr);
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }

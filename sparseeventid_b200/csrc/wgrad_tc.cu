@@ -324,8 +324,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
 }
 
 // dW[k] += sum over the CTAs of offset k of their slabs (4 floats per thread, slabs added in CTA order: deterministic)
+// Block 0 also finishes the convolution's bias gradient when the column sums of dout are already known (they come out
+// of the BatchNorm backward that produced dout): dbias (+)= colsum, folded in here instead of one more launch.
 __global__ void k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dW, int K, int CC, int s_other, int s_centre,
-                               int centre) {
+                               int centre, const float* __restrict__ colsum, float* dbias, int nbias, int accumulate_bias) {
+  if (blockIdx.x == 0 && colsum != nullptr)
+    for (int c = threadIdx.x; c < nbias; c += blockDim.x) dbias[c] = (accumulate_bias ? dbias[c] : 0.f) + colsum[c];
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
   if (i >= (int64_t)K * CC) return;
   const int k = (int)(i / CC);
@@ -365,7 +369,17 @@ float* wgrad_slabs(size_t bytes, cudaStream_t s) {
   return p;
 }
 
+struct BiasFold { const float* colsum; float* dbias; int C; int accumulate; };
+static thread_local BiasFold g_fold = {nullptr, nullptr, 0, 0};
+
 }  // namespace wg
+
+// module_api.cu: "dbias (+)= colsum" is pending for the next weight-gradient launch of this thread; scn_wgrad_tc folds
+// it into its reduction kernel when it runs one (and clears it), otherwise the caller does it itself.
+void scn_wgrad_set_bias_fold(const float* colsum, float* dbias, int C, int accumulate) {
+  wg::g_fold = {colsum, dbias, C, accumulate};
+}
+bool scn_wgrad_bias_fold_pending() { return wg::g_fold.colsum != nullptr; }
 
 bool scn_wgrad_tc_enabled() {
   static int v = -1;
@@ -444,7 +458,10 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
     kern<<<grid, wg::THREADS, smem, s>>>(p);
     SCN_LAUNCH_CHECK();
     if (p.part != nullptr) {
-      wg::k_wgrad_reduce<<<grid_for((int64_t)K * CC / 4, 256), 256, 0, s>>>(p.part, dW, K, CC, p.s_other, p.s_centre, p.centre);
+      const wg::BiasFold bf = wg::g_fold;
+      wg::g_fold = {nullptr, nullptr, 0, 0};
+      wg::k_wgrad_reduce<<<grid_for((int64_t)K * CC / 4, 256), 256, 0, s>>>(p.part, dW, K, CC, p.s_other, p.s_centre, p.centre,
+                                                                            bf.colsum, bf.dbias, bf.C, bf.accumulate);
       SCN_LAUNCH_CHECK();
     }
     return SCN_OK;

@@ -112,22 +112,17 @@ struct ConvFn : public torch::autograd::Function<ConvFn> {
       colsum = bc.colsum;
     bc.dx = at::Tensor();
     bc.colsum = at::Tensor();
-    const bool own_db = need_db && !colsum.defined();
-    double* ws = own_db ? stats_scratch(x.device(), cout).data_ptr<double>() : nullptr;
+    double* ws = need_db ? stats_scratch(x.device(), cout).data_ptr<double>() : nullptr;
     TORCH_CHECK(!need_dx || has(wimg_t), "scn_b200: dgrad needs the transposed weight-image workspace");
-    check(scn_conv_module_backward(x.data_ptr(), dcode(x), x.size(0), dout.data_ptr(), dcode(dout),
+    check(scn_conv_module_backward_colsum(x.data_ptr(), dcode(x), x.size(0), dout.data_ptr(), dcode(dout),
                                    ctx->saved_data["n_out_rows"].toInt(), nbr_fwd.data_ptr<int32_t>(), nbr_fwd.size(1),
                                    nbr_bwd.data_ptr<int32_t>(), nbr_bwd.size(1), (int)K, (int)cin, (int)cout,
                                    weight.data_ptr<float>(), ctx->saved_data["mirror"].toBool() ? 1 : 0,
                                    (int)ctx->saved_data["prec"].toInt(), optr(wimg_t), ctx->saved_data["skip_prep"].toBool() ? 1 : 0, optr(dx),
                                    wtarget->defined() ? wtarget->data_ptr<float>() : nullptr, gw.defined() ? 0 : 1,
-                                   own_db && btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0, ws,
-                                   cur_stream()),
-          "scn_conv_module_backward");
-    if (colsum.defined()) {
-      if (gb.defined()) gb.add_(colsum.view_as(gb));
-      else db = colsum.view_as(bias);
-    }
+                                   btarget->defined() ? btarget->data_ptr<float>() : nullptr, gb.defined() ? 1 : 0,
+                                   colsum.defined() ? colsum.data_ptr<float>() : nullptr, ws, cur_stream()),
+          "scn_conv_module_backward_colsum");
     if (gw.defined()) grad_ready(weight);
     if (gb.defined()) grad_ready(bias);
     return {dx, dw, db, at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(), at::Tensor(),

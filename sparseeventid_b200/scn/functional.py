@@ -192,16 +192,10 @@ def _conv_backward(ctx, dout):
         if not (need_db and bdx is not None and bdx.data_ptr() == dout.data_ptr() and bdx.shape == dout.shape
                 and colsum.numel() == cout):
             colsum = None
-        own_db = need_db and colsum is None
         dx = ops.conv_module_backward(xw, dout, weight, ctx.nbr_fwd, ctx.nbr_bwd, ctx.n_out_rows, K, cin, cout,
                                       ctx.mirror, ctx.prec, wimg_t, skip, need_dx,
                                       gw if gw is not None else dw, gw is None,
-                                      (gb if gb is not None else db) if own_db else None, gb is not None)
-        if colsum is not None:
-            if gb is not None:
-                gb.add_(colsum.view_as(gb))
-            else:
-                db = colsum.view_as(bias)
+                                      gb if gb is not None else db, gb is not None, colsum)
         if dx is not None and dx.dtype != x.dtype:
             dx = ops.convert(dx, x.dtype)
         if gw is not None:

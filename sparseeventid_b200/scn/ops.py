@@ -276,17 +276,19 @@ def conv_module_forward(x, weight, bias, nbr, n_out_rows, K, cin, cout, prec, ou
 
 
 def conv_module_backward(x, dout, weight, nbr_fwd, nbr_bwd, n_out_rows, K, cin, cout, mirror, prec, wimg_t, skip_prep,
-                         need_dx, dw, zero_dw, dbias, accumulate_dbias):
-    """One C-ABI call: dx (returned, or None), dW accumulated into `dw`, dbias (+)= column sums.  Any part may be None."""
+                         need_dx, dw, zero_dw, dbias, accumulate_dbias, dout_colsum=None):
+    """One C-ABI call: dx (returned, or None), dW accumulated into `dw`, dbias (+)= column sums of dout (taken from
+    `dout_colsum` when the caller already has them).  Any part may be None."""
     dx = torch.empty((x.shape[0], cin), dtype=x.dtype, device=x.device) if need_dx else None
     ws = stats_scratch(x.device, cout) if dbias is not None else None
-    L.check(L.lib().scn_conv_module_backward(
+    L.check(L.lib().scn_conv_module_backward_colsum(
         x.data_ptr(), _DT[x.dtype], x.shape[0], dout.data_ptr(), _DT[dout.dtype], n_out_rows,
         nbr_fwd.data_ptr(), nbr_fwd.shape[1], nbr_bwd.data_ptr(), nbr_bwd.shape[1], K, cin, cout, weight.data_ptr(),
         int(mirror), prec, None if wimg_t is None else wimg_t.data_ptr(), int(skip_prep),
         None if dx is None else dx.data_ptr(), None if dw is None else dw.data_ptr(), int(zero_dw),
-        None if dbias is None else dbias.data_ptr(), int(accumulate_dbias), None if ws is None else ws.data_ptr(),
-        L.stream()), "scn_conv_module_backward")
+        None if dbias is None else dbias.data_ptr(), int(accumulate_dbias),
+        None if dout_colsum is None else dout_colsum.data_ptr(), None if ws is None else ws.data_ptr(),
+        L.stream()), "scn_conv_module_backward_colsum")
     return dx
 
 

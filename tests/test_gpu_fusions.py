@@ -104,3 +104,34 @@ def test_batched_weight_images_equal_per_module_images(scn):
         F.release_weight_images()
     finally:
         scn.set_precision("fp32")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_batchnorm_calls_with_changing_channel_counts(scn, dtype):
+    """The two-launch BatchNorm alternates between two sets of accumulators and each call's apply kernel clears the set
+    the NEXT call will use -- as far as the PREVIOUS call wrote it.  A sequence whose channel count goes up and down
+    (the backward pass of the encoder does) must give the textbook result at every call."""
+    from sparseeventid_b200.scn import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for i, (n, c) in enumerate([(3000, 160), (5000, 32), (900, 192), (4000, 64), (7000, 32), (2500, 128), (6000, 96), (64, 32)]):
+        x = (torch.randn(n, c, device="cuda", generator=g) * 1.5 - 0.3).to(dtype)
+        d = torch.randn(n, c, device="cuda", generator=g).to(dtype)
+        gamma = torch.rand(c, device="cuda", generator=g) + 0.5
+        beta = torch.randn(c, device="cuda", generator=g) * 0.1
+        rm, rv = torch.zeros(c, device="cuda"), torch.ones(c, device="cuda")
+        out, stats = ops.bn_forward(x, gamma, beta, rm, rv, True, 1e-4, 0.9, 0.333)
+        xd = x.double()
+        mean, var = xd.mean(0), xd.var(0, unbiased=False)
+        xh = (xd - mean) / torch.sqrt(var + 1e-4)
+        y = xh * gamma.double() + beta.double()
+        ref = torch.where(y > 0, y, y * 0.333)
+        tol = 8e-3 if dtype == torch.bfloat16 else 2e-5
+        assert float((out.double() - ref).norm() / ref.norm()) <= tol, ("forward", i, n, c)
+        assert float((stats[0].double() - mean).abs().max()) <= 1e-5 * float(mean.abs().max() + 1), ("mean", i, n, c)
+        assert float((stats[1].double() * torch.sqrt(var + 1e-4) - 1).abs().max()) <= 1e-5, ("invstd", i, n, c)
+        if i % 2 == 0:                                   # odd / even mixes forward and backward calls on the two sets
+            dx, dg, db = ops.bn_backward(x, d, gamma, beta, stats, True, 0.333)
+            dl = torch.where(y > 0, d.double(), d.double() * 0.333)
+            dref = gamma.double() / torch.sqrt(var + 1e-4) * (dl - dl.mean(0) - xh * (dl * xh).mean(0))
+            assert float((dx.double() - dref).norm() / dref.norm()) <= tol, ("backward", i, n, c)
+            assert float((db.double() - dl.sum(0)).abs().max()) <= 1e-4 * float(dl.abs().sum(0).max()), ("dbeta", i, n, c)

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--depth", type=int, default=9)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--out", default=os.path.join("gpurun_out", "fullres_inference.json"))
+    ap.add_argument("--bytes-per-event", type=float, default=0.0, help="measured at a smaller batch: enables the memory guard")
     a = ap.parse_args()
     scn.set_precision("bf16")
     cfg = legacy.LegacyNetworkConfig(n_initial_filters=32, network_depth=a.depth, res_blocks_per_layer=2,
@@ -38,6 +39,12 @@ def main():
     coords = torch.from_numpy(np.ascontiguousarray(c)).cuda()
     feats = torch.from_numpy(np.ascontiguousarray(f)).float().cuda()
     n = coords.shape[0]
+    if a.bytes_per_event > 0:                 # memory guard for the large batches: never drive the box out of memory
+        free, total = torch.cuda.mem_get_info()
+        need = a.bytes_per_event * a.batch * 1.2
+        if need > 0.85 * free:
+            print(json.dumps({"batch": a.batch, "skipped": f"predicted {need / 1e9:.0f} GB > 85% of the free {free / 1e9:.0f} GB"}))
+            return
     torch.cuda.reset_peak_memory_stats()
     base = torch.cuda.memory_allocated()
     with torch.no_grad():
@@ -57,10 +64,12 @@ def main():
            "batch": a.batch, "voxels": n, "voxels_per_event": n / a.batch, "ms_per_batch": ms,
            "events_per_s": a.batch / (ms * 1e-3), "peak_bytes_above_weights_and_input": peak,
            "bytes_per_event": per_event, "max_batch_180GB_extrapolated": int(170e9 / per_event),
+           "hbm_peak_allocated_GB": torch.cuda.max_memory_allocated() / 1e9,
            "max_batch_per_call": 65535, "logits_finite": bool(all(torch.isfinite(v).all() for v in out.values()))}
     print(json.dumps(res))
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
-    json.dump(res, open(a.out, "w"), indent=1)
+    with open(a.out, "a") as fo:
+        fo.write(json.dumps(res) + "\n")
 
 
 if __name__ == "__main__":
