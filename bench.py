@@ -73,17 +73,49 @@ def host_batch(batch, seed, dataset):
     return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
 
 
+# ns of step time per active site of resolution level l (B200, measured per-level kernel times of the bench step
+# divided by the level's rows: convolutions fwd + dgrad + wgrad and BatchNorm; the two deepest levels are latency-bound
+# and do not depend on their row counts)
+LEVEL_COST_NS = (6.1, 11.0, 22.6, 35.0)
+
+
+def event_cost(arr, dataset):
+    """Cost proxy of every event of a larcv batch array [n][planes][voxels][D+1]: the sum over the resolution levels of
+    (active sites of the level) x (measured ns per site).  Equal level-0 voxel counts still leave the step times of the
+    ranks +-6% apart (8 GPUs: the slowest rank cost 1.3 ms of a 20 ms step) because the deeper levels' sizes depend on
+    how the event is spread in space; their site counts follow from the coordinates alone (floor(x / 2^l), unique)."""
+    from sparseeventid_b200 import synthetic
+    n = arr.shape[0]
+    cost = np.zeros(n)
+    for e in range(n):
+        for pl in range(arr.shape[1]):
+            v = arr[e, pl]
+            live = v[:, -1] != synthetic.PAD
+            c = v[live, :-1].astype(np.int64)
+            if c.shape[0] == 0:
+                continue
+            if dataset == "dune2d":                  # 2-D planes: [1,2,2] downsampling, the plane axis is not strided
+                c = c[:, -2:]
+            for l, w in enumerate(LEVEL_COST_NS):
+                q = c >> l
+                key = q[:, 0]
+                for a in range(1, q.shape[1]):
+                    key = key * 65536 + q[:, a]
+                cost[e] += w * np.unique(key).shape[0]
+    return cost
+
+
 def balanced_host_batch(batch, world, rank, seed, dataset):
-    """Event-sharded data parallelism with voxel-count balancing: the global batch of batch x world events
-    is dealt to the ranks in a snake over the events sorted by active-site count, so every rank gets the same number of
-    events AND (within ~0.2%) the same number of voxels.  Contiguous sharding of DUNE-like events leaves the heaviest of 8
+    """Event-sharded data parallelism with work balancing: the global batch of batch x world events
+    is dealt to the ranks in a snake over the events sorted by a cost proxy (event_cost), so every rank gets the same
+    number of events AND nearly the same work.  Contiguous sharding of DUNE-like events leaves the heaviest of 8
     ranks 12% above the mean, and a synchronous step runs at the pace of the heaviest rank.  Deterministic: every rank
     generates the same global batch from the seed and keeps its share."""
     from sparseeventid_b200 import synthetic
     from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
     n = batch * world
     arr = synthetic.larcv_batch_3d(n, seed=seed) if dataset == "dune3d" else synthetic.larcv_batch_2d(n, seed=seed)
-    counts = (arr[..., -1] != synthetic.PAD).sum(axis=(1, 2))
+    counts = event_cost(arr, dataset)
     order = np.argsort(-counts, kind="stable")
     mine = []
     for j, e in enumerate(order):
@@ -199,7 +231,8 @@ def sharding_text(args, world):
         return "identical batches on every rank (diagnostic)"
     if args.no_balance:
         return "contiguous by event"
-    return "by event, dealt in a snake over the voxel-count order (equal events and ~equal voxels per rank)"
+    return ("by event, dealt in a snake over the order of a per-event cost proxy (sites of resolution levels 0-3 x measured "
+            "ns per site): equal events and ~equal work per rank")
 
 
 def run_reference(args, rank):

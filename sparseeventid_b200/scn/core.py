@@ -278,12 +278,13 @@ class Pending:
     BatchNormalization -> LeakyReLU/ReLU and AddTable -> LeakyReLU/ReLU run as ONE kernel each (forward and
     backward) instead of two.  Any other consumer reads ``.features``, which runs the deferred layer unfused."""
 
-    __slots__ = ("kind", "run", "fuse")
+    __slots__ = ("kind", "run", "fuse", "rerun")
 
-    def __init__(self, kind, run, fuse):
+    def __init__(self, kind, run, fuse, rerun=None):
         self.kind = kind        # "bn" | "add"
         self.run = run          # () -> features, the layer as written
         self.fuse = fuse        # (leak) -> features of layer followed by leaky ReLU
+        self.rerun = rerun or run   # the layer as written, evaluated a SECOND time (no side effects: running statistics)
 
 
 class SparseConvNetTensor:
@@ -313,7 +314,7 @@ class SparseConvNetTensor:
             self._pending = None
         elif self._features is None and self._taken is not None:
             # a second consumer of a tensor whose layer was fused into a following activation: run it as written
-            self._features = self._taken.run()
+            self._features = self._taken.rerun()
             self._taken = None
         return self._features
 

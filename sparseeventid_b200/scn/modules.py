@@ -275,21 +275,24 @@ class BatchNormalization(nn.Module):
         assert x.nelement() == 0 or x.size(1) == self.nPlanes
         training = self.training
 
-        def run(leak=float(self.leakiness)):
+        def run(leak=float(self.leakiness), second=False):
+            # second=True: the same layer evaluated again for another consumer of a tensor whose first evaluation was
+            # fused into a following activation -- the running statistics were updated by the first one
+            rm = self.running_mean.clone() if second and training else self.running_mean
+            rv = self.running_var.clone() if second and training else self.running_var
             ext = _ext.get()
             w, b = self.weight, self.bias
             if (ext is not None and x.is_cuda and not ops.profiling()
                     and (w is None or (w.dtype == torch.float32 and w.is_contiguous() and b.dtype == torch.float32
                                        and b.is_contiguous()))):
-                return ext.batch_norm(x, w, b, self.running_mean, self.running_var, training, float(self.eps),
+                return ext.batch_norm(x, w, b, rm, rv, training, float(self.eps),
                                       float(self.momentum), leak,
                                       w is not None and getattr(w, "_scn_direct_grad", False)
                                       and getattr(b, "_scn_direct_grad", False))
-            return F.BatchNormFn.apply(x, w, b, self.running_mean, self.running_var, training,
-                                       float(self.eps), float(self.momentum), leak)
+            return F.BatchNormFn.apply(x, w, b, rm, rv, training, float(self.eps), float(self.momentum), leak)
         if config.fusion_enabled() and float(self.leakiness) == 1.0:
             # defer by one module: a following LeakyReLU/ReLU becomes the fused leakiness of this same kernel
-            return SparseConvNetTensor(None, input.metadata, input.spatial_size, Pending("bn", run, run), input._spc)
+            return SparseConvNetTensor(None, input.metadata, input.spatial_size, Pending("bn", run, run, lambda: run(second=True)), input._spc)
         return _new_like(input, run())
 
     def __repr__(self):

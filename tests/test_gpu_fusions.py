@@ -135,3 +135,22 @@ def test_batchnorm_calls_with_changing_channel_counts(scn, dtype):
             dref = gamma.double() / torch.sqrt(var + 1e-4) * (dl - dl.mean(0) - xh * (dl * xh).mean(0))
             assert float((dx.double() - dref).norm() / dref.norm()) <= tol, ("backward", i, n, c)
             assert float((db.double() - dl.sum(0)).abs().max()) <= 1e-4 * float(dl.abs().sum(0).max()), ("dbeta", i, n, c)
+
+
+def test_second_consumer_of_a_fused_batchnorm_does_not_update_running_statistics_again(scn):
+    """BatchNormalization -> LeakyReLU runs as one kernel; a second reader of the BatchNorm's own output makes the layer
+    run once more as written.  The running statistics must have been updated exactly once (SCN: one module call)."""
+    scn.set_precision("fp32")
+    torch.manual_seed(1)
+    c = 32
+    coords = torch.as_tensor(blob_sites(300, (16, 16, 16), 2, seed=3)).cuda()
+    feats = (torch.randn(coords.shape[0], c) * 2 + 1).cuda()
+    x = scn.InputLayer(3, [16, 16, 16])((coords, feats, 2))
+    bn = scn.BatchNormalization(c).cuda().train()
+    y = bn(x)
+    z = scn.LeakyReLU()(y)
+    fused = z.features
+    plain = y.features                        # second consumer: the BatchNorm as written
+    want_mean = 0.1 * x.features.float().mean(0)
+    assert torch.allclose(bn.running_mean, want_mean, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(torch.where(plain > 0, plain, plain * 0.333), fused, rtol=1e-5, atol=1e-6)
