@@ -718,25 +718,34 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
   const int nch = (n_in + tc::KC - 1) / tc::KC;
   p.last_kc = n_in - (nch - 1) * tc::KC;
   p.num_tiles = (int)((n_rows + tc::BM - 1) / tc::BM);
-  // tiles per group: as many accumulators as fit in half of TMEM (weight-tile reuse, and one issuing warp per
-  // tile up to MMA_WARPS); the tiles themselves are split evenly over the CTAs, so T does not unbalance the grid
-  int T = 256 / n_out;
-  if (T < 1) T = 1;
-  if (T > 8) T = 8;
-  p.nbuf = 2;
+  // Tiles per group.  A group's T tiles are dealt to NM = 1, 2 or 4 classes (one issuing warp + producer group each) and
+  // every class walks its tiles' stages as ONE serial chain (~1400 cycles per stage), so a CTA's time is, in units of
+  // one tile's chain,   sum over its groups of ceil(tiles of the group / NM)   -- T = 5 on 4 classes costs 2 units per
+  // group, like T = 8 -- plus the epilogue of every group where it is not overlapped (one group in all 512 TMEM columns
+  // instead of two alternating halves).  T is the candidate that minimises that estimate for the CTA with the most
+  // tiles; ties go to the larger T (fewer passes over the weight image).  Measured, 96 channels: 138 k rows (8 tiles per
+  // CTA) T = 5 -> 4: 108 -> 84 us; 155 k rows (9 tiles per CTA): T = 5 stays, 111 us.
   int max_ctas = kNumSMs;
   if (force_grid > 0 && force_grid < max_ctas) max_ctas = force_grid;
   const int per_cta = (p.num_tiles + max_ctas - 1) / max_ctas;
+  const int q_per_tile = (tc_pair(n_in) ? (K + 1) / 2 : K) * nch;
+  int T = 1;
+  p.nbuf = 2;
   {
-    // One group in all 512 TMEM columns instead of two alternating halves: the epilogue then no longer overlaps the
-    // next group's MMAs, but T doubles (more issuing warps, more weight-tile reuse).  Worth it when a CTA has a
-    // single group anyway, or when half of TMEM holds fewer than three tiles (n_out >= 96: the weight tiles are
-    // half or more of the bytes a CTA pulls from L2; measured 146 -> 120 us at 155 k rows x 96 channels).
-    int t1 = 512 / n_out;
-    if (t1 > 8) t1 = 8;
-    if (t1 > T && (per_cta <= t1 || T <= 2)) { T = t1; p.nbuf = 1; }
+    double best = 1e30;
+    for (int t = 1; t <= 8 && t * n_out <= 512 && t <= (per_cta > 0 ? per_cta : 1); ++t) {
+      const int nm = t >= 4 ? 4 : (t >= 2 ? 2 : 1);
+      const int full = per_cta / t, rem = per_cta % t;
+      const int groups = full + (rem ? 1 : 0);
+      const double units = (double)full * ((t + nm - 1) / nm) + (rem ? (rem + nm - 1) / nm : 0);
+      const int nbuf = t * n_out <= 256 ? 2 : 1;
+      // epilogue of a group (~600 cycles per tile and 32 output columns) relative to a tile's chain; hidden behind the
+      // next group's main loop when double-buffered, except for the last group
+      const double ep = (double)t * (n_out / 32.0) * 600.0 / ((double)q_per_tile * 1400.0);
+      const double cost = units + (nbuf == 1 ? groups * ep : ep + 0.15 * (groups - 1) * ep);
+      if (cost <= best + 1e-9) { best = cost; T = t; p.nbuf = nbuf; }
+    }
   }
-  if (T > per_cta) T = per_cta;
   if (force_t > 0) {
     T = force_t;
     if (T > 8) T = 8;

@@ -148,7 +148,7 @@ def test_second_consumer_of_a_fused_batchnorm_does_not_update_running_statistics
     x = scn.InputLayer(3, [16, 16, 16])((coords, feats, 2))
     bn = scn.BatchNormalization(c).cuda().train()
     y = bn(x)
-    z = scn.LeakyReLU()(y)
+    z = scn.LeakyReLU(0.333)(y)
     fused = z.features
     plain = y.features                        # second consumer: the BatchNorm as written
     want_mean = 0.1 * x.features.float().mean(0)
