@@ -60,17 +60,17 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------- data
 
 
-def host_batch(batch, seed, dataset):
+def host_batch(batch, seed, dataset, raw=False):
     """Synthetic larcv batch -> SCN input tuple exactly as the reference's transform produces it
-    (coords float64 [N,4] with the batch index last, features float32 [N,1]) + 4 label vectors."""
+    (coords float64 [N,4] with the batch index last, features float32 [N,1]) + 4 label vectors
+    (+ the raw -999-padded larcv batch-filler array itself with raw=True)."""
     from sparseeventid_b200 import synthetic
     from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d, larcvsparse_to_scnsparse_3d
-    if dataset == "dune3d":
-        coords, feats, bs = larcvsparse_to_scnsparse_3d(synthetic.larcv_batch_3d(batch, seed=seed))
-    else:
-        coords, feats, bs = larcvsparse_to_scnsparse_2d(synthetic.larcv_batch_2d(batch, seed=seed))
+    arr = synthetic.larcv_batch_3d(batch, seed=seed) if dataset == "dune3d" else synthetic.larcv_batch_2d(batch, seed=seed)
+    coords, feats, bs = larcvsparse_to_scnsparse_3d(arr) if dataset == "dune3d" else larcvsparse_to_scnsparse_2d(arr)
     labels = synthetic.make_labels(batch, seed=seed)
-    return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
+    out = (np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels)
+    return out + (arr,) if raw else out
 
 
 # ns of step time per active site of resolution level l (B200, measured per-level kernel times of the bench step
@@ -105,7 +105,7 @@ def event_cost(arr, dataset):
     return cost
 
 
-def balanced_host_batch(batch, world, rank, seed, dataset):
+def balanced_host_batch(batch, world, rank, seed, dataset, raw=False):
     """Event-sharded data parallelism with work balancing: the global batch of batch x world events
     is dealt to the ranks in a snake over the events sorted by a cost proxy (event_cost), so every rank gets the same
     number of events AND nearly the same work.  Contiguous sharding of DUNE-like events leaves the heaviest of 8
@@ -127,7 +127,8 @@ def balanced_host_batch(batch, world, rank, seed, dataset):
     sub = np.ascontiguousarray(arr[mine])
     coords, feats, bs = larcvsparse_to_scnsparse_3d(sub) if dataset == "dune3d" else larcvsparse_to_scnsparse_2d(sub)
     labels = {k: v[mine] for k, v in synthetic.make_labels(n, seed=seed).items()}
-    return np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels
+    out = (np.ascontiguousarray(coords, dtype=np.float64), np.ascontiguousarray(feats, dtype=np.float32), bs, labels)
+    return out + (sub,) if raw else out
 
 
 class ClockSampler:
@@ -309,18 +310,25 @@ def run_ours(args, rank, world, local_rank):
     pool = []
     for i in range(args.pool):
         if world > 1 and args.same_batches:          # diagnostic: every rank steps through the SAME batches (no straggler term)
-            coords, feats, bs, labels = host_batch(args.batch, 1234 + 1000 * i, args.dataset)
+            coords, feats, bs, labels, arr = host_batch(args.batch, 1234 + 1000 * i, args.dataset, raw=True)
         elif world > 1 and not args.no_balance:
-            coords, feats, bs, labels = balanced_host_batch(args.batch, world, rank, 1234 + 1000 * i, args.dataset)
+            coords, feats, bs, labels, arr = balanced_host_batch(args.batch, world, rank, 1234 + 1000 * i, args.dataset, raw=True)
         else:
-            coords, feats, bs, labels = host_batch(args.batch, 1234 + 100000 * rank + 1000 * i, args.dataset)
+            coords, feats, bs, labels, arr = host_batch(args.batch, 1234 + 100000 * rank + 1000 * i, args.dataset, raw=True)
         h = {"coords": torch.from_numpy(coords).pin_memory(), "feats": torch.from_numpy(feats).pin_memory(),
-             "labels": {k: torch.from_numpy(v).pin_memory() for k, v in labels.items()}, "bs": bs}
+             "labels": {k: torch.from_numpy(v).pin_memory() for k, v in labels.items()}, "bs": bs,
+             "larcv": torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()}
         pool.append(h)
     dpool = [{"coords": h["coords"].to(dev), "feats": h["feats"].to(dev),
               "labels": {k: v.to(dev) for k, v in h["labels"].items()}, "bs": h["bs"]} for h in pool]
     n_voxels = int(np.mean([h["coords"].shape[0] for h in pool]))
-    h2d_bytes = int(np.mean([h["coords"].numel() * 8 + h["feats"].numel() * 4 + 4 * 8 * args.batch for h in pool]))
+    # e2e input: the raw larcv batch-filler array (what src/io/larcv_fetcher.py:394-419 hands to the transform), copied as
+    # it is and compacted on the GPU (scn_larcv_count / scn_larcv_compact); --e2e-tuple uploads the host-transformed
+    # SCN tuple instead (coords float64 [N,4] + features)
+    if args.e2e_tuple:
+        h2d_bytes = int(np.mean([h["coords"].numel() * 8 + h["feats"].numel() * 4 + 4 * 8 * args.batch for h in pool]))
+    else:
+        h2d_bytes = int(np.mean([h["larcv"].numel() * 4 + 4 * 8 * args.batch for h in pool]))
 
     # Both loops tell the trainer which batch comes next (what a data loader with one batch of look-ahead knows), so the
     # next step's rulebooks -- a function of coordinates only -- are built on the rulebook stream during this step's
@@ -334,13 +342,19 @@ def run_ours(args, rank, world, local_rank):
 
     copy_stream = torch.cuda.Stream(device=dev)
     staged = {}
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_2d_gpu, larcvsparse_to_scnsparse_3d_gpu
+    to_scn_gpu = larcvsparse_to_scnsparse_3d_gpu if args.dataset == "dune3d" else larcvsparse_to_scnsparse_2d_gpu
 
     def upload(i):
         """H2D of step i's inputs from pinned host memory on a copy stream -> (batch tuple, labels, done event)."""
         h = pool[i % len(pool)]
         with torch.cuda.stream(copy_stream):
-            c = h["coords"].to(dev, non_blocking=True)
-            f = h["feats"].to(dev, non_blocking=True)
+            if args.e2e_tuple:
+                c = h["coords"].to(dev, non_blocking=True)
+                f = h["feats"].to(dev, non_blocking=True)
+            else:                   # device-side twin of the reference's transform; one row count comes back to the host
+                raw_dev = h["larcv"].to(dev, non_blocking=True)
+                c, f = to_scn_gpu(raw_dev)[:2]
             lab = {k: v.to(dev, non_blocking=True) for k, v in h["labels"].items()}
             ev = copy_stream.record_event()
         return (c, f, h["bs"]), lab, ev
@@ -545,6 +559,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": 4,
+                    "input": ("host-transformed SCN tuple (coords float64 [N,4], features fp32)" if args.e2e_tuple else
+                              "raw larcv batch-filler array [B, planes, 50000, D+1] fp32 (-999 padded) from pinned host memory, "
+                              "transformed on the GPU (scn_larcv_count / scn_larcv_compact)"),
                     "d2h": "every step's loss -> pinned host memory inside the timed region, consumed one step later",
                     "loss_first_last": [losses[0], losses[-1]] if losses else None,
                     "losses_finite": bool(np.all(np.isfinite(losses)))},
@@ -574,6 +591,7 @@ def main():
     ap.add_argument("--no-prefetch", action="store_true", help="do not build the next batch's rulebooks ahead")
     ap.add_argument("--no-balance", action="store_true", help="N>1: contiguous event sharding instead of voxel-count balancing")
     ap.add_argument("--same-batches", action="store_true", help="N>1 diagnostic: identical batches on every rank")
+    ap.add_argument("--e2e-tuple", action="store_true", help="e2e uploads the host-transformed SCN tuple instead of the raw larcv array")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
