@@ -132,7 +132,11 @@ def balanced_host_batch(batch, world, rank, seed, dataset, raw=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    """SM clocks / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line), every
+    200 ms.  In-process through NVML (nvidia_ml_py) when it is importable: an `nvidia-smi -lms 100` child process was
+    measured to cost the timed loop up to 20% in some runs (2533-2648 vs 3260-3310 events/s in the same build, the e2e
+    loop without a sampler stable at 3214-3371); nvidia-smi remains the fallback.  The NVML queries are the same ones
+    nvidia-smi makes (clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -141,22 +145,68 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []          # NVML path: (sm MHz, max MHz, watts, reasons bitmask)
+        self.nvml = None
+        self.stop_flag = False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu_index])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu_index
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self._physical_index())], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append((n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                     n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM),
+                                     n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0,
+                                     int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))))
+            except Exception:
+                pass
+            time.sleep(0.2)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": n.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksEventReasonSwPowerCap}
+            reasons = sorted(k for k, b in bits.items() if any(s[3] & b for s in self.samples))
+            return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
+                    "power_w_max": float(max(s[2] for s in self.samples)), "samples": len(self.samples), "reasons": reasons,
+                    "source": "NVML in-process, every 200 ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -180,7 +230,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 # ------------------------------------------------------------------------------------ CPU arm
@@ -427,11 +477,15 @@ def run_ours(args, rank, world, local_rank):
         step_e2e(i)
     staged.clear(); loss_pending.clear(); losses.clear()
     torch.cuda.synchronize()
-    for i in range(args.warmup):
-        step_resident(i)
+    # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up steps: its start-up (process launch, NVML
+    # initialisation) takes driver locks for a few hundred ms and was measured to cost the first timed loop up to 15%
+    # when it fell inside it (2825 vs 3272 events/s in one process); it keeps sampling through the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)
+    for i in range(args.warmup):
+        step_resident(i)
     ms, launches = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps)

@@ -20,6 +20,43 @@ extern unsigned long long g_scn_launch_count;
     if (e__ != cudaSuccess) return (int)e__;              \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A training step is ~830 dependent launches; between two of them the GPU drains the first grid, flushes, and only then
+// starts scheduling the second (~2-3 us each).  The hot-path kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: a kernel signals griddepcontrol.launch_dependents as its first
+// instruction, so the NEXT kernel's CTAs are scheduled onto SMs as this one's CTAs retire and run their prologue
+// (barrier init, TMEM allocation, coefficient loads from parameters) early; every kernel executes griddepcontrol.wait
+// -- all prerequisite grids complete and their memory visible -- BEFORE its first access to global memory that a
+// preceding kernel may have written or may still read, so results do not change.  A dependent grid is only launched
+// once every CTA of its primary has started, so a waiting CTA never starves the grid it waits for.  The instructions
+// are no-ops for a kernel launched the ordinary way.  SCN_B200_PDL=0 turns the attribute off.
+#include <cstdlib>
+#include <utility>
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+inline bool scn_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SCN_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t scn_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = scn_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 static constexpr uint64_t kEmptyKey = ~0ull;
 static constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 

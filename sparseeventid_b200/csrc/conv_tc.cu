@@ -101,6 +101,7 @@ struct Params {
 template <int NCH, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   extern __shared__ unsigned char smem_raw[];
+  pdl_launch_dependents();                                 // the next kernel's CTAs may be scheduled as ours retire (common.cuh)
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;            // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* gbase = smem_raw + (base - raw);
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_conv_tc(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                              // barrier init and TMEM allocation above overlapped the previous kernel's tail
 
   // Classes: tile t of a group belongs to class t mod NM (NM = 1, 2 or 4).  A class is an independent pipeline: ONE issuing
   // warp, NGRP / NM producer groups and a private ring of SA / NM A slots.  Every slot therefore has a single consumer
@@ -803,7 +805,7 @@ int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nb
     }
   }
   auto launch = [&](auto kern) -> int {
-    kern<<<grid, tc::THREADS, smem, s>>>(p);
+    SCN_CUDA(scn_launch_pdl(kern, dim3((unsigned)grid), dim3(tc::THREADS), smem, s, p));
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   };

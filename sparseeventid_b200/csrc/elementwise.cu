@@ -610,6 +610,8 @@ __device__ __forceinline__ float inv_sqrt_refined(double v) {
 template <typename T>
 __global__ void __launch_bounds__(256, 4) k_bn_stats2(const T* __restrict__ x, int64_t n, int C, double* acc) {
   __shared__ float sred[256 * 16];
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const bool active = ty < RY;
@@ -653,6 +655,8 @@ __global__ void __launch_bounds__(256, 4) k_bn_apply2(const T* __restrict__ x, i
                                                       float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                                       const double* __restrict__ acc, double* __restrict__ acc_other,
                                                       int zero_n, double inv_n, T* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const int64_t stride = (int64_t)gridDim.x * RY;
@@ -720,6 +724,8 @@ __global__ void __launch_bounds__(256, 3) k_bn_bwd_stats2(const T* __restrict__ 
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float leak, double* acc) {
   __shared__ float sred[256 * 16];
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const bool active = ty < RY;
@@ -783,6 +789,8 @@ __global__ void __launch_bounds__(256, COLSUM ? 3 : 4) k_bn_bwd_apply2(const T* 
                                                           float* dbeta, int accumulate, double* colacc, unsigned* ticket,
                                                           float* __restrict__ colsum) {
   __shared__ float sred[COLSUM ? 256 * 8 : 1];
+  pdl_launch_dependents();
+  pdl_wait();
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
   const bool active = ty < RY;
@@ -1005,6 +1013,8 @@ __global__ void k_acc_to_float(const double* __restrict__ acc, int C, float* dga
 
 template <typename T, int VEC>
 __global__ void k_leaky_fwd(const T* __restrict__ x, int64_t nvec, float leak, T* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   float v[VEC];
@@ -1016,6 +1026,8 @@ __global__ void k_leaky_fwd(const T* __restrict__ x, int64_t nvec, float leak, T
 template <typename T, int VEC>
 __global__ void k_leaky_bwd(const T* __restrict__ x, const T* __restrict__ dout, int64_t nvec, float leak,
                             T* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   float v[VEC], d[VEC];
@@ -1028,6 +1040,8 @@ __global__ void k_leaky_bwd(const T* __restrict__ x, const T* __restrict__ dout,
 template <typename T, int VEC>
 __global__ void k_add_fwd(const T* __restrict__ a, const T* __restrict__ b, int64_t nvec, float leak,
                           T* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= nvec) return;
   float v[VEC], w[VEC];
@@ -1162,10 +1176,10 @@ int bn_forward_t(const T* x, int64_t n, int C, const float* gamma, const float* 
     const unsigned ph = bn_next_phase(s, C, &zero_n);
     double* acc = zws + (ph ? kAcc1 : 0);
     double* other = zws + (ph ? 0 : kAcc1);
-    k_bn_stats2<T><<<g, 256, 0, s>>>(x, n, C, acc);
+    SCN_CUDA(scn_launch_pdl(k_bn_stats2<T>, dim3((unsigned)g), dim3(256), 0, s, x, n, C, acc));
     SCN_LAUNCH_CHECK();
-    k_bn_apply2<T><<<g, 256, 0, s>>>(x, n, C, gamma, beta, rm, rv, eps, momentum, leak, save_mean, save_invstd, acc, other,
-                                     zero_n, 1.0 / (double)n, out);
+    SCN_CUDA(scn_launch_pdl(k_bn_apply2<T>, dim3((unsigned)g), dim3(256), 0, s, x, n, C, gamma, beta, rm, rv, eps, momentum, leak,
+                            save_mean, save_invstd, (const double*)acc, other, zero_n, 1.0 / (double)n, out));
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }
@@ -1229,14 +1243,17 @@ int bn_backward_t(const T* x, const T* dout, int64_t n, int C, const float* gamm
     double* other = zws + (ph ? 0 : kAcc1);
     double* colacc = zws + 2 * 2048;                                   // shared with k_col_sum_fused (stream-ordered)
     unsigned* ticket = reinterpret_cast<unsigned*>(zws + 3 * 2048 + 1);
-    k_bn_bwd_stats2<T><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc);
+    SCN_CUDA(scn_launch_pdl(k_bn_bwd_stats2<T>, dim3((unsigned)bn_grid2(n, ry, 3)), dim3(256), 0, s, x, dout, n, C, mean, invstd,
+                            gamma, beta, leak, acc));
     SCN_LAUNCH_CHECK();
     if (colsum)
-      k_bn_bwd_apply2<T, true><<<bn_grid2(n, ry, 3), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc, other,
-                                                                  zero_n, dx, dgamma, dbeta, accumulate, colacc, ticket, colsum);
+      SCN_CUDA(scn_launch_pdl(k_bn_bwd_apply2<T, true>, dim3((unsigned)bn_grid2(n, ry, 3)), dim3(256), 0, s, x, dout, n, C, mean,
+                              invstd, gamma, beta, leak, (const double*)acc, other, zero_n, dx, dgamma, dbeta, accumulate,
+                              colacc, ticket, colsum));
     else
-      k_bn_bwd_apply2<T, false><<<bn_grid2(n, ry, 4), 256, 0, s>>>(x, dout, n, C, mean, invstd, gamma, beta, leak, acc, other,
-                                                                   zero_n, dx, dgamma, dbeta, accumulate, colacc, ticket, nullptr);
+      SCN_CUDA(scn_launch_pdl(k_bn_bwd_apply2<T, false>, dim3((unsigned)bn_grid2(n, ry, 4)), dim3(256), 0, s, x, dout, n, C, mean,
+                              invstd, gamma, beta, leak, (const double*)acc, other, zero_n, dx, dgamma, dbeta, accumulate,
+                              colacc, ticket, (float*)nullptr));
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }
@@ -1302,9 +1319,9 @@ int ew_launch3(int which, const T* a, const T* b, int64_t count, float leak, T* 
   if (vec && count % 8 == 0) {                 // 16-byte accesses for bf16, 2 x 16 bytes for fp32
     const int64_t n8 = count / 8;
     const unsigned g8 = grid_for(n8, 256);
-    if (which == 0) k_leaky_fwd<T, 8><<<g8, 256, 0, s>>>(a, n8, leak, out);
-    else if (which == 1) k_leaky_bwd<T, 8><<<g8, 256, 0, s>>>(a, b, n8, leak, out);
-    else k_add_fwd<T, 8><<<g8, 256, 0, s>>>(a, b, n8, leak, out);
+    if (which == 0) SCN_CUDA(scn_launch_pdl(k_leaky_fwd<T, 8>, dim3(g8), dim3(256), 0, s, a, n8, leak, out));
+    else if (which == 1) SCN_CUDA(scn_launch_pdl(k_leaky_bwd<T, 8>, dim3(g8), dim3(256), 0, s, a, b, n8, leak, out));
+    else SCN_CUDA(scn_launch_pdl(k_add_fwd<T, 8>, dim3(g8), dim3(256), 0, s, a, b, n8, leak, out));
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }

@@ -82,6 +82,7 @@ template <int NA, int NB, bool HALF, int PAIRS>
 __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
   constexpr int BLK_BYTES = PAIRS * 128;                 // one 64-channel block of a stage: PAIRS rows x 128 B
   extern __shared__ unsigned char smem_raw[];
+  pdl_launch_dependents();                               // see common.cuh: programmatic dependent launch
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   unsigned char* gbase = smem_raw + (base - raw);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                            // everything above overlapped the previous kernel's tail
 
   if (warp >= EPI_WARPS && warp < EPI_WARPS + PROD_WARPS) {
     // ================================ producers =============================================
@@ -328,6 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_wgrad_tc(const Params p) {
 // of the BatchNorm backward that produced dout): dbias (+)= colsum, folded in here instead of one more launch.
 __global__ void k_wgrad_reduce(const float* __restrict__ part, float* __restrict__ dW, int K, int CC, int s_other, int s_centre,
                                int centre, const float* __restrict__ colsum, float* dbias, int nbias, int accumulate_bias) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x == 0 && colsum != nullptr)
     for (int c = threadIdx.x; c < nbias; c += blockDim.x) dbias[c] = (accumulate_bias ? dbias[c] : 0.f) + colsum[c];
   const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
@@ -455,13 +459,13 @@ int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_
   p.part = use_slabs ? wg::wgrad_slabs((size_t)grid * CC * sizeof(float), s) : nullptr;
   auto launch = [&](auto kern) -> int {
     SCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, wg::THREADS, smem, s>>>(p);
+    SCN_CUDA(scn_launch_pdl(kern, dim3((unsigned)grid), dim3(wg::THREADS), smem, s, p));
     SCN_LAUNCH_CHECK();
     if (p.part != nullptr) {
       const wg::BiasFold bf = wg::g_fold;
       wg::g_fold = {nullptr, nullptr, 0, 0};
-      wg::k_wgrad_reduce<<<grid_for((int64_t)K * CC / 4, 256), 256, 0, s>>>(p.part, dW, K, CC, p.s_other, p.s_centre, p.centre,
-                                                                            bf.colsum, bf.dbias, bf.C, bf.accumulate);
+      SCN_CUDA(scn_launch_pdl(wg::k_wgrad_reduce, dim3(grid_for((int64_t)K * CC / 4, 256)), dim3(256), 0, s, (const float*)p.part, dW,
+                              K, CC, p.s_other, p.s_centre, p.centre, bf.colsum, bf.dbias, bf.C, bf.accumulate));
       SCN_LAUNCH_CHECK();
     }
     return SCN_OK;
