@@ -133,7 +133,7 @@ def balanced_host_batch(batch, world, rank, seed, dataset, raw=False):
 
 class ClockSampler:
     """SM clocks / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line), every
-    200 ms.  In-process through NVML (nvidia_ml_py) when it is importable: an `nvidia-smi -lms 100` child process was
+    300 ms.  In-process through NVML (nvidia_ml_py) when it is importable: an `nvidia-smi -lms 100` child process was
     measured to cost the timed loop up to 20% in some runs (2533-2648 vs 3260-3310 events/s in the same build, the e2e
     loop without a sampler stable at 3214-3371); nvidia-smi remains the fallback.  The NVML queries are the same ones
     nvidia-smi makes (clocks.sm, clocks.max.sm, power.draw, clocks_event_reasons)."""
@@ -163,6 +163,10 @@ class ClockSampler:
             import pynvml
             pynvml.nvmlInit()
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            # the maximum SM clock is a constant of the board: queried ONCE, before the timed region -- under load
+            # nvmlDeviceGetMaxClockInfo takes 2 ms (median) to 90 ms and stalls kernel launches meanwhile (it made one
+            # step of the timed loop 70-120 ms long in 3 runs of 5); current clock, power and event reasons take ~10 us
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
             self.nvml = pynvml
             self.t = threading.Thread(target=self._poll, daemon=True)
             self.t.start()
@@ -182,13 +186,14 @@ class ClockSampler:
         n = self.nvml
         while not self.stop_flag:
             try:
-                self.samples.append((n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM),
-                                     n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM),
-                                     n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0,
-                                     int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))))
+                mode = os.environ.get("SCN_BENCH_SAMPLER", "all")          # diagnostic: which NVML query perturbs the loop
+                clk = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM) if mode != "none" else 0
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0 if mode in ("all", "power") else 0.0
+                rs = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if mode in ("all", "reasons") else 0
+                self.samples.append((clk, self.max_mhz, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.3)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -206,7 +211,7 @@ class ClockSampler:
             reasons = sorted(k for k, b in bits.items() if any(s[3] & b for s in self.samples))
             return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
                     "power_w_max": float(max(s[2] for s in self.samples)), "samples": len(self.samples), "reasons": reasons,
-                    "source": "NVML in-process, every 200 ms"}
+                    "source": "NVML in-process (clock, power, event reasons), every 300 ms; max clock read once before"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -452,16 +457,25 @@ def run_ours(args, rank, world, local_rank):
         finally:
             gc.enable()
 
+    step_times = []
+
     def _timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]      # per-step marks: diagnostics only
         l0 = lib.scn_launch_count()
         e0.record()
         for i in range(steps):
             fn(i)
+            marks[i].record()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
+        prev, per_step = e0, []
+        for m in marks:
+            per_step.append(prev.elapsed_time(m))
+            prev = m
+        step_times.append([round(v, 2) for v in per_step])
         launches = lib.scn_launch_count() - l0
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -621,6 +635,8 @@ def run_ours(args, rank, world, local_rank):
                     "losses_finite": bool(np.all(np.isfinite(losses)))},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+            "step_ms_median_max": [[round(float(np.median(t)), 2), round(float(np.max(t)), 2)] for t in step_times],
+            "step_ms_resident": step_times[0] if step_times else None,
             "rulebook_ms": round(sum(v["ms_per_step"] for k, v in (breakdown or {}).items() if k.startswith("rulebook")), 3),
             "rulebook_ms_note": "hash build + InputLayer rules + all submanifold / strided neighbour tables of one batch, GPU time on the rulebook stream (overlaps the feature kernels)",
             "roofline": roof,

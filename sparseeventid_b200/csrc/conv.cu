@@ -70,6 +70,8 @@ template <typename TI, typename TO, int NOUT>
 __global__ void __launch_bounds__(256) k_conv_cin1(const TI* __restrict__ in, const int32_t* __restrict__ nbr, int K,
                                                    int64_t n_rows, int64_t n_pad, const float* __restrict__ B,
                                                    const float* __restrict__ bias, TO* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_w[];          // [K][NOUT]
   for (int i = threadIdx.x; i < K * NOUT; i += blockDim.x) s_w[i] = B[i];
   __syncthreads();
@@ -99,6 +101,8 @@ template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) k_wgrad_generic(const TI* __restrict__ in, const TO* __restrict__ dout,
                                                        const int32_t* __restrict__ nbr, int64_t n_rows, int64_t n_pad,
                                                        int n_in, int n_out, int chunk, float* __restrict__ dW) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ int s_list[];   // compacted (in,out) pairs of this chunk: [2][chunk]
   __shared__ int s_count;
   const int k = blockIdx.y;
@@ -496,9 +500,9 @@ int conv_generic_t(const TI* in, const int32_t* nbr, int K, int64_t n_rows, int6
   if (n_in == 1 && (n_out == 16 || n_out == 32 || n_out == 64) && (size_t)K * n_out * 4 <= 48 * 1024) {
     const size_t smem = (size_t)K * n_out * sizeof(float);
     const unsigned g = grid_for(n_rows, 256);
-    if (n_out == 16) k_conv_cin1<TI, TO, 16><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
-    else if (n_out == 32) k_conv_cin1<TI, TO, 32><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
-    else k_conv_cin1<TI, TO, 64><<<g, 256, smem, s>>>(in, nbr, K, n_rows, n_pad, B, bias, out);
+    if (n_out == 16) SCN_CUDA(scn_launch_pdl(k_conv_cin1<TI, TO, 16>, dim3(g), dim3(256), smem, s, in, nbr, K, n_rows, n_pad, B, bias, out));
+    else if (n_out == 32) SCN_CUDA(scn_launch_pdl(k_conv_cin1<TI, TO, 32>, dim3(g), dim3(256), smem, s, in, nbr, K, n_rows, n_pad, B, bias, out));
+    else SCN_CUDA(scn_launch_pdl(k_conv_cin1<TI, TO, 64>, dim3(g), dim3(256), smem, s, in, nbr, K, n_rows, n_pad, B, bias, out));
     SCN_LAUNCH_CHECK();
     return SCN_OK;
   }
@@ -513,8 +517,8 @@ int wgrad_generic_t(const TI* in, const TO* dout, const int32_t* nbr, int K, int
                     int n_out, float* dW, cudaStream_t s) {
   const int chunk = 512;
   dim3 grid((unsigned)((n_rows + chunk - 1) / chunk), (unsigned)K);
-  k_wgrad_generic<TI, TO><<<grid, 256, 2 * chunk * sizeof(int), s>>>(in, dout, nbr, n_rows, n_pad, n_in, n_out, chunk,
-                                                                     dW);
+  SCN_CUDA(scn_launch_pdl(k_wgrad_generic<TI, TO>, grid, dim3(256), 2 * chunk * sizeof(int), s, in, dout, nbr, n_rows, n_pad, n_in,
+                          n_out, chunk, dW));
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }

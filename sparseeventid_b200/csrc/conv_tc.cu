@@ -583,6 +583,8 @@ __global__ void k_prep_weights_tc(const float* __restrict__ W, int K, int Cin, i
 // of W[k][c][n] are coalesced over n and the transposed image reads 32 contiguous bytes per thread.  (One thread per
 // ELEMENT with 2-byte scattered stores took 360 us per step for the 41 M elements of the default network.)
 __global__ void __launch_bounds__(256) k_prep_weights_tc_batched(const long long* __restrict__ descs, int n, long long units) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= units) return;
   const long long e = i * 8;
@@ -630,8 +632,8 @@ __global__ void __launch_bounds__(256) k_prep_weights_tc_batched(const long long
 extern "C" int scn_conv_prep_weights_batched(const void* descs, int n, int64_t total, void* stream) {
   if (n <= 0 || total <= 0) return SCN_OK;
   if (!descs) return SCN_ERR_ARG;
-  tc::k_prep_weights_tc_batched<<<grid_for(total / 8, 256), 256, 0, (cudaStream_t)stream>>>((const long long*)descs, n,
-                                                                                           (long long)(total / 8));
+  SCN_CUDA(scn_launch_pdl(tc::k_prep_weights_tc_batched, dim3(grid_for(total / 8, 256)), dim3(256), 0, (cudaStream_t)stream,
+                          (const long long*)descs, n, (long long)(total / 8)));
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }

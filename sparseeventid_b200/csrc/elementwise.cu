@@ -869,6 +869,8 @@ __global__ void __launch_bounds__(256, COLSUM ? 3 : 4) k_bn_bwd_apply2(const T* 
 template <typename T>
 __global__ void __launch_bounds__(256) k_col_sum_fused(const T* __restrict__ x, int64_t n, int C, double* acc,
                                                        unsigned* ticket, float* __restrict__ out, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sred[];                        // [RY][CV][8]
   const int CV = C >> 3, RY = 256 / CV;
   const int tx = threadIdx.x % CV, ty = threadIdx.x / CV;
@@ -1398,10 +1400,10 @@ extern "C" int scn_col_sum_acc(const void* x, int dtype, int64_t n, int C, doubl
       if (g < 1) g = 1;
       const size_t smem = (size_t)ry * (C >> 3) * 8 * sizeof(float);
       if (dtype == SCN_F32)
-        k_col_sum_fused<float><<<(unsigned)g, 256, smem, s>>>((const float*)x, n, C, acc1, ticket, out, accumulate);
+        SCN_CUDA(scn_launch_pdl(k_col_sum_fused<float>, dim3((unsigned)g), dim3(256), smem, s, (const float*)x, n, C, acc1, ticket, out, accumulate));
       else if (dtype == SCN_BF16)
-        k_col_sum_fused<__nv_bfloat16><<<(unsigned)g, 256, smem, s>>>((const __nv_bfloat16*)x, n, C, acc1, ticket, out,
-                                                                        accumulate);
+        SCN_CUDA(scn_launch_pdl(k_col_sum_fused<__nv_bfloat16>, dim3((unsigned)g), dim3(256), smem, s, (const __nv_bfloat16*)x, n, C, acc1,
+                                ticket, out, accumulate));
       else
         return SCN_ERR_ARG;
       SCN_LAUNCH_CHECK();

@@ -87,6 +87,8 @@ __device__ __forceinline__ int hash_insert_min_group8(uint64_t* tk, int32_t* tv,
 
 __global__ void k_insert(const uint64_t* __restrict__ keys, int64_t n, uint64_t* tk, int32_t* tv, uint32_t bucket_mask,
                          int32_t* __restrict__ slot_of) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t i = t >> 3;
   bool active = i < n;
@@ -107,6 +109,8 @@ __global__ void k_lookup(const uint64_t* __restrict__ q, int64_t n, const uint64
 
 __global__ void k_first_flag(const int32_t* __restrict__ slot_of, const int32_t* __restrict__ tv, int64_t n,
                              int32_t* __restrict__ flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) flag[i] = (tv[slot_of[i]] == (int)i) ? 1 : 0;
 }
@@ -115,6 +119,8 @@ __global__ void k_assign_rows(const uint64_t* __restrict__ keys, const int32_t* 
                               const int32_t* __restrict__ tv, const int32_t* __restrict__ flag,
                               const int32_t* __restrict__ rank, int64_t n, int32_t* __restrict__ row_of_input,
                               uint64_t* __restrict__ keys_out, int32_t* __restrict__ n_active) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int first = tv[slot_of[i]];
@@ -125,6 +131,8 @@ __global__ void k_assign_rows(const uint64_t* __restrict__ keys, const int32_t* 
 
 __global__ void k_store_rows(const int32_t* __restrict__ slot_of, const int32_t* __restrict__ flag,
                              const int32_t* __restrict__ rank, int64_t n, int32_t* tv) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n && flag[i]) tv[slot_of[i]] = rank[i];
 }
@@ -193,7 +201,7 @@ extern "C" int scn_hash_build(const uint64_t* keys, int64_t n, uint64_t* table_k
   int rc = clear_table(table_keys, table_vals, capacity, s);
   if (rc) return rc;
   if (n == 0) return SCN_OK;
-  k_insert<<<grid_for(n * 8, 256), 256, 0, s>>>(keys, n, table_keys, table_vals, (uint32_t)(capacity / 8 - 1), nullptr);
+  SCN_CUDA(scn_launch_pdl(k_insert, dim3(grid_for(n * 8, 256)), dim3(256), 0, s, keys, n, table_keys, table_vals, (uint32_t)(capacity / 8 - 1), (int32_t*)nullptr));
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }
@@ -232,15 +240,15 @@ extern "C" int scn_input_layer_rules(const uint64_t* keys_in, int64_t n, uint64_
   void* tmp = w + 3 * seg;
   size_t tmp_bytes = scan_temp_bytes(n);
   uint32_t bm = (uint32_t)(capacity / 8 - 1);
-  k_insert<<<grid_for(n * 8, 256), 256, 0, s>>>(keys_in, n, table_keys, table_vals, bm, slot_of);
+  SCN_CUDA(scn_launch_pdl(k_insert, dim3(grid_for(n * 8, 256)), dim3(256), 0, s, keys_in, n, table_keys, table_vals, bm, slot_of));
   SCN_LAUNCH_CHECK();
-  k_first_flag<<<grid_for(n, 256), 256, 0, s>>>(slot_of, table_vals, n, flag);
+  SCN_CUDA(scn_launch_pdl(k_first_flag, dim3(grid_for(n, 256)), dim3(256), 0, s, slot_of, table_vals, n, flag));
   SCN_LAUNCH_CHECK();
   SCN_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, flag, rank, (int)n, s));
-  k_assign_rows<<<grid_for(n, 256), 256, 0, s>>>(keys_in, slot_of, table_vals, flag, rank, n, row_of_input, keys_out,
-                                                 n_active_dev);
+  SCN_CUDA(scn_launch_pdl(k_assign_rows, dim3(grid_for(n, 256)), dim3(256), 0, s, keys_in, slot_of, table_vals, flag, rank, n,
+                          row_of_input, keys_out, n_active_dev));
   SCN_LAUNCH_CHECK();
-  k_store_rows<<<grid_for(n, 256), 256, 0, s>>>(slot_of, flag, rank, n, table_vals);
+  SCN_CUDA(scn_launch_pdl(k_store_rows, dim3(grid_for(n, 256)), dim3(256), 0, s, slot_of, flag, rank, n, table_vals));
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }

@@ -13,6 +13,8 @@ namespace {
 __global__ void k_subm_probe(const uint64_t* __restrict__ keys, int64_t n, const uint64_t* __restrict__ tk,
                              const int32_t* __restrict__ tv, uint32_t bucket_mask, int f0, int f1, int f2, int K,
                              int32_t* __restrict__ nbr, int64_t n_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half = (K - 1) / 2;
   int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t item = t >> 2;
@@ -42,6 +44,8 @@ __global__ void k_subm_probe(const uint64_t* __restrict__ keys, int64_t n, const
 }
 
 __global__ void k_identity_rows(int32_t* __restrict__ dst, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (int)i;
 }
@@ -78,6 +82,8 @@ __global__ void k_assign_coarse(const uint64_t* __restrict__ sorted, const int32
 __global__ void k_strided_tables(const int32_t* __restrict__ out_row_of_in, const int32_t* __restrict__ off_of_in,
                                  int64_t n_in, int32_t* __restrict__ down, int64_t n_out_pad,
                                  int32_t* __restrict__ up, int64_t n_in_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n_in) return;
   int q = out_row_of_in[i], k = off_of_in[i];
@@ -153,12 +159,11 @@ extern "C" int scn_subm_rulebook(const uint64_t* keys, int64_t n, const uint64_t
   if (n == 0) return SCN_OK;
   if (!keys || !table_keys || !table_vals) return SCN_ERR_ARG;
   const int half = (K - 1) / 2;
-  k_identity_rows<<<grid_for(n, 256), 256, 0, s>>>(nbr + (int64_t)half * n_pad, n);
+  SCN_CUDA(scn_launch_pdl(k_identity_rows, dim3(grid_for(n, 256)), dim3(256), 0, s, nbr + (int64_t)half * n_pad, n));
   SCN_LAUNCH_CHECK();
   if (half > 0) {
-    k_subm_probe<<<grid_for((int64_t)half * n * 4, 256), 256, 0, s>>>(keys, n, table_keys, table_vals,
-                                                                      (uint32_t)(capacity / 8 - 1), f0, f1, f2, K, nbr,
-                                                                      n_pad);
+    SCN_CUDA(scn_launch_pdl(k_subm_probe, dim3(grid_for((int64_t)half * n * 4, 256)), dim3(256), 0, s, keys, n, table_keys,
+                            table_vals, (uint32_t)(capacity / 8 - 1), f0, f1, f2, K, nbr, n_pad));
     SCN_LAUNCH_CHECK();
   }
   return SCN_OK;
@@ -210,6 +215,8 @@ extern "C" int scn_strided_rulebook(const uint64_t* keys_in, int64_t n, int s0, 
 namespace {
 __global__ void k_coarse_keys_off(const uint64_t* __restrict__ keys, int64_t n, int s0, int s1, int s2,
                                   uint64_t* __restrict__ qkeys, int32_t* __restrict__ off) {
+  pdl_launch_dependents();
+  pdl_wait();
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   int x0, x1, x2, b;
@@ -234,7 +241,7 @@ extern "C" int scn_strided_rulebook_hash(const uint64_t* keys_in, int64_t n, int
   uint64_t* qkeys = (uint64_t*)workspace;
   char* ws2 = (char*)workspace + round_up_i64(n * 8, 256);
   if (n > 0) {
-    k_coarse_keys_off<<<grid_for(n, 256), 256, 0, s>>>(keys_in, n, s0, s1, s2, qkeys, off_of_in);
+    SCN_CUDA(scn_launch_pdl(k_coarse_keys_off, dim3(grid_for(n, 256)), dim3(256), 0, s, keys_in, n, s0, s1, s2, qkeys, off_of_in));
     SCN_LAUNCH_CHECK();
   }
   return scn_input_layer_rules(qkeys, n, table_keys, table_vals, capacity, out_row_of_in, keys_out, n_out_dev, ws2,
@@ -249,8 +256,8 @@ extern "C" int scn_strided_tables(const int32_t* out_row_of_in, const int32_t* o
   if (nbr_down && n_out_pad) SCN_CUDA(cudaMemsetAsync(nbr_down, 0xff, (size_t)K * n_out_pad * sizeof(int32_t), s));
   if (nbr_up && n_in_pad) SCN_CUDA(cudaMemsetAsync(nbr_up, 0xff, (size_t)K * n_in_pad * sizeof(int32_t), s));
   if (n_in == 0) return SCN_OK;
-  k_strided_tables<<<grid_for(n_in, 256), 256, 0, s>>>(out_row_of_in, off_of_in, n_in, nbr_down, n_out_pad, nbr_up,
-                                                       n_in_pad);
+  SCN_CUDA(scn_launch_pdl(k_strided_tables, dim3(grid_for(n_in, 256)), dim3(256), 0, s, out_row_of_in, off_of_in, n_in, nbr_down,
+                          n_out_pad, nbr_up, n_in_pad));
   SCN_LAUNCH_CHECK();
   return SCN_OK;
 }
