@@ -72,6 +72,7 @@ class SparseDenseTensor(torch.Tensor):
         r._pooled_mean = pooled_mean
         r._dense = None
         r._batch_of_row = None
+        r._pooled_cache = None
         return r
 
     # -- helpers -------------------------------------------------------------------------------
@@ -127,7 +128,11 @@ class SparseDenseTensor(torch.Tensor):
                     vol = 1
                     for v in self._spatial:
                         vol *= v
-                    pooled = self._pooled_mean(self._rows_f32(), self._batch_index(), self._batch, vol)
+                    # the reference applies one full-extent pool per head (classification_head.py:19-28: four heads on the
+                    # same tensor): the pooled mean is computed once and shared (autograd sums the heads' gradients)
+                    pooled = self._pooled_cache
+                    if pooled is None:
+                        pooled = self._pooled_cache = self._pooled_mean(self._rows_f32(), self._batch_index(), self._batch, vol)
                     return pooled.view((self._batch, pooled.shape[1]) + (1,) * len(self._spatial))
 
         # anything else: behave exactly like the dense tensor

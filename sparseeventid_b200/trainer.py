@@ -205,6 +205,8 @@ class Trainer:
         self.prefetch_thread = os.environ.get("SCN_B200_PREFETCH_THREAD", "0") not in ("0", "false", "False")
         self._prefetch_thread = None
         self._prefetch_error = None
+        self.graph_head = os.environ.get("SCN_B200_GRAPH_HEAD", "1") not in ("0", "false", "False")
+        self._head_graphs = {}
         self.model.train()
 
     def save_checkpoint(self, path: str) -> None:
@@ -266,6 +268,56 @@ class Trainer:
             if err is not None:
                 raise err
 
+    # ---- dense heads + focal loss as ONE CUDA graph per direction ------------------------------------------------------
+    # classification_head.py:19-28 + supervised_eventID.py:168-196 on a [B, 128] pooled tensor are ~90 tiny torch launches
+    # forward and ~150 backward, a few microseconds each with a launch gap after every one.  Their shapes are static (batch
+    # size, channel count), so they are captured once with torch.cuda.make_graphed_callables (dropout included: the
+    # capture registers the CUDA generator, every replay draws fresh random numbers) and replayed; the encoder -- whose
+    # level sizes are data-dependent -- stays eager.  Eager fallback for anything unexpected (a different batch size, CPU,
+    # a head that does not start with the full-extent pool, SCN_B200_GRAPH_HEAD=0).
+    def _graphed_head_loss(self, feat, labels):
+        if not self.graph_head or self.device.type != "cuda" or not isinstance(feat, torch.Tensor):
+            return None
+        heads = getattr(self.model.head, "classification_head", None)
+        if heads is None or any(not isinstance(h[0], torch.nn.AvgPool3d) for h in heads.values()):
+            return None
+        keys = list(heads.keys())
+        if any(k not in labels for k in keys):
+            return None
+        first = heads[keys[0]][0]
+        pooled = first(feat)                                    # [B, C, 1, 1, 1]; the lazy dense view pools the sparse rows
+        labs = tuple(labels[k] for k in keys)
+        sig = (tuple(pooled.shape), pooled.dtype) + tuple((tuple(l.shape), l.dtype) for l in labs)
+        g = self._head_graphs.get(sig)
+        if g is None:
+            if len(self._head_graphs) >= 4:
+                return None
+
+            class HeadLoss(torch.nn.Module):
+                def __init__(self, heads, keys):
+                    super().__init__()
+                    self.tails = torch.nn.ModuleList([heads[k][1:] for k in keys])
+
+                def forward(self, pooled, *labs):
+                    loss = 0.0
+                    for tail, lab in zip(self.tails, labs):
+                        logits = tail(pooled)
+                        y = torch.nn.functional.one_hot(lab, logits.size(-1))
+                        p = torch.nn.functional.softmax(logits, dim=-1).clamp(1e-7, 1.0 - 1e-7)
+                        loss = loss + (-y * torch.log(p) * (1 - p) ** 2).sum(dim=-1).mean()
+                    return loss
+
+            try:
+                mod = HeadLoss(heads, keys)
+                mod.train(self.model.head.training)
+                sample = (pooled.detach().clone().requires_grad_(True),) + tuple(l.clone() for l in labs)
+                g = torch.cuda.make_graphed_callables(mod, sample)
+            except Exception:                                   # capture is an optimisation, never a requirement
+                self.graph_head = False
+                return None
+            self._head_graphs[sig] = g
+        return g(pooled, *labs)
+
     def step(self, batch, labels, prefetch=None, prefetch_ready=None):
         """batch: (coords [N,4], features [N,1], batch_size) on self.device; labels: dict of int64 [B].
         prefetch: the next step's batch tuple (same tensor objects that will be passed then), optional."""
@@ -277,8 +329,10 @@ class Trainer:
                 self._convs = [m for m in self.model.modules() if hasattr(m, "mirror_dgrad") and hasattr(m, "workspace")]
             prep(self._convs)
         try:
-            logits = self.model(batch)
-            loss = networks.focal_loss(labels, logits)
+            feat = self.model.encoder(batch)
+            loss = self._graphed_head_loss(feat, labels)
+            if loss is None:
+                loss = networks.focal_loss(labels, self.model.head(feat))
             if prefetch is not None:
                 if self.prefetch_thread and self.device.type == "cuda":
                     self._prefetch_async(prefetch, prefetch_ready)

@@ -154,3 +154,35 @@ def test_second_consumer_of_a_fused_batchnorm_does_not_update_running_statistics
     want_mean = 0.1 * x.features.float().mean(0)
     assert torch.allclose(bn.running_mean, want_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(torch.where(plain > 0, plain, plain * 0.333), fused, rtol=1e-5, atol=1e-6)
+
+
+def test_graphed_head_and_loss_match_eager(scn):
+    """Trainer replays the dense heads + focal loss as CUDA graphs; with dropout off (head.eval()) loss, gradients and
+    the parameters after two optimizer steps must equal the eager path's."""
+    import numpy as np
+    from sparseeventid_b200 import synthetic
+    from sparseeventid_b200.data_transforms import larcvsparse_to_scnsparse_3d
+    from sparseeventid_b200.trainer import Trainer
+    scn.set_precision("bf16")
+    try:
+        c, f, bs = larcvsparse_to_scnsparse_3d(synthetic.larcv_batch_3d(4, seed=77))
+        batch = (torch.from_numpy(np.ascontiguousarray(c, dtype=np.float64)).cuda(),
+                 torch.from_numpy(np.ascontiguousarray(f, dtype=np.float32)).cuda(), bs)
+        labels = {k: torch.from_numpy(v).cuda() for k, v in synthetic.make_labels(4, seed=77).items()}
+        out = []
+        for graph in (True, False):
+            tr = Trainer(scn, "dune3d", device="cuda", seed=0)
+            tr.graph_head = graph
+            tr.model.head.eval()
+            losses = [float(tr.step(batch, labels)) for _ in range(2)]
+            assert bool(tr._head_graphs) == graph
+            out.append((losses, [p.detach().clone() for p in tr.model.head.parameters()],
+                        tr.arena.flat.detach().clone()))
+        (la, pa, ga), (lb, pb, gb) = out
+        assert np.allclose(la, lb, rtol=1e-5, atol=1e-7), (la, lb)
+        for x, y in zip(pa, pb):
+            assert torch.allclose(x, y, rtol=1e-4, atol=1e-6)
+        scale = float(gb.abs().max())
+        assert float((ga - gb).abs().max()) <= 2e-3 * scale          # encoder gradients: bf16 kernels with atomics-free but order-dependent sums
+    finally:
+        scn.set_precision("fp32")
