@@ -12,6 +12,12 @@ bool scn_tc_shape_ok(int K, int n_in, int n_out);
 size_t scn_tc_image_bytes(int K, int n_in, int n_out);
 int scn_tc_prep(const float* W, int K, int Cin, int Cout, int transpose, int mirror, void* out, cudaStream_t s);
 bool scn_wgrad_tc_enabled();
+bool scn_stem_tc_enabled();                       // stem_tc.cu
+bool scn_stem_tc_shape_ok(int K, int n_in, int n_out);
+int scn_stem_tc_forward(const void* x, int x_dtype, const int32_t* nbr, int K, int64_t n_rows, int64_t n_pad, const float* W,
+                        const float* bias, __nv_bfloat16* out, cudaStream_t s);
+int scn_stem_tc_wgrad(const void* x, int x_dtype, const __nv_bfloat16* dout, const int32_t* nbr, int K, int64_t n_rows,
+                      int64_t n_pad, float* dW, cudaStream_t s);
 int scn_wgrad_tc(const __nv_bfloat16* x, const __nv_bfloat16* dout, const int32_t* nbr, int K, int64_t n_rows,
                  int64_t n_pad, int Cin, int Cout, float* dW, cudaStream_t s);
 int scn_tc_forward(const __nv_bfloat16* in, int64_t n_in_rows, const int32_t* nbr, int K, int64_t n_rows,
@@ -582,6 +588,10 @@ extern "C" int scn_conv_forward(const void* in, int in_dtype, int64_t n_in_rows,
   }
   if (mma_ok(K, n_in, n_out, precision)) return SCN_ERR_UNSUPPORTED;   // Bprep is bf16 for this shape
   const float* B = (const float*)Bprep;
+  // the stem (one input channel) as a dense GEMM over the neighbour table on tensor cores (stem_tc.cu); the exact fp32
+  // mode keeps the FFMA kernel
+  if (precision != SCN_PREC_FP32 && out_dtype == SCN_BF16 && scn_stem_tc_enabled() && scn_stem_tc_shape_ok(K, n_in, n_out))
+    return scn_stem_tc_forward(in, in_dtype, nbr, K, n_out_rows, n_pad, B, bias, (__nv_bfloat16*)out, s);
   if (in_dtype == SCN_F32 && out_dtype == SCN_F32)
     return conv_generic_t<float, float>((const float*)in, nbr, K, n_out_rows, n_pad, n_in, n_out, B, bias, (float*)out, s);
   if (in_dtype == SCN_F32 && out_dtype == SCN_BF16)
@@ -610,6 +620,10 @@ extern "C" int scn_conv_wgrad(const void* in, int in_dtype, const void* dout, in
     int rc = scn_wgrad_tc((const __nv_bfloat16*)in, (const __nv_bfloat16*)dout, nbr, K, n_rows, n_pad, n_in, n_out, dW, s);
     if (rc != SCN_ERR_UNSUPPORTED) return rc;
   }
+  // the stem (one input channel): dense GEMM over the neighbour table on tensor cores (stem_tc.cu)
+  if (precision != SCN_PREC_FP32 && dout_dtype == SCN_BF16 && (n_pad & 127) == 0 && scn_stem_tc_enabled() &&
+      scn_stem_tc_shape_ok(K, n_in, n_out))
+    return scn_stem_tc_wgrad(in, in_dtype, (const __nv_bfloat16*)dout, nbr, K, n_rows, n_pad, dW, s);
   if (mma_ok(K, n_in, n_out, precision) && in_dtype == dout_dtype) {
     if (in_dtype == SCN_F32)
       return wgrad_mma_t<float>((const float*)in, (const float*)dout, nbr, K, n_rows, n_pad, n_in, n_out, dW, s);

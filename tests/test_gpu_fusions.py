@@ -186,3 +186,37 @@ def test_graphed_head_and_loss_match_eager(scn):
         assert float((ga - gb).abs().max()) <= 2e-3 * scale          # encoder gradients: bf16 kernels with atomics-free but order-dependent sums
     finally:
         scn.set_precision("fp32")
+
+
+@pytest.mark.parametrize("n,K", [(5000, 125), (333, 125), (2048, 25), (17, 9)])
+def test_stem_tensor_core_kernels(scn, n, K):
+    """csrc/stem_tc.cu: the one-input-channel stem as dense GEMMs over the neighbour table (bf16 hi/lo splits of the fp32
+    input and weights, fp32 accumulation) against float64: the forward within bf16 output rounding, the weight gradient
+    within 1e-5 of its scale."""
+    from sparseeventid_b200 import _lib as L
+    from sparseeventid_b200.scn import ops
+    g = torch.Generator(device="cuda").manual_seed(n * 7 + K)
+    n_pad = ops.pad128(n)
+    nbr = torch.full((K, n_pad), -1, dtype=torch.int32, device="cuda")
+    live = torch.rand(K, n, device="cuda", generator=g) < 0.16
+    idx = torch.randint(0, n, (K, n), device="cuda", generator=g, dtype=torch.int32)
+    nbr[:, :n] = torch.where(live, idx, torch.full_like(idx, -1))
+    nbr[K // 2, :n] = torch.arange(n, device="cuda", dtype=torch.int32)
+    x = torch.randn(n, 1, device="cuda", generator=g) * 3 + 1
+    w = torch.randn(K, 1, 32, device="cuda", generator=g) * 0.2
+    bias = torch.randn(32, device="cuda", generator=g)
+    dout = torch.randn(n, 32, device="cuda", generator=g).bfloat16()
+    prec = L.PREC_BF16
+    assert ops.conv_path(K, 1, 32, prec, torch.bfloat16) == 0            # not a tcgen05 shape: the stem path decides
+    bp = ops.prep_weights(w.reshape(K, 1, 32).contiguous(), False, False, prec, torch.bfloat16)
+    out = ops.conv_forward(x, nbr, n, 1, 32, bp, bias, prec, torch.bfloat16)
+    j = nbr[:, :n].long()
+    xg = torch.where(j >= 0, x.double()[:, 0][j.clamp_min(0)], torch.zeros((), dtype=torch.float64, device="cuda"))   # [K, n]
+    ref = bias.double()[None, :] + torch.einsum("kn,kc->nc", xg, w.double()[:, 0, :])
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 6e-3, ("forward", n, K, err)                           # bf16 output: half an ulp = 2^-9
+    assert float((out.double() - ref).norm() / ref.norm()) <= 3e-3
+    dw = ops.conv_wgrad(x, dout, nbr, n, 1, 32, prec)
+    dref = torch.einsum("kn,nc->kc", xg, dout.double())
+    derr = float((dw.double()[:, 0, :] - dref).abs().max() / dref.abs().max())
+    assert derr <= 1e-5, ("wgrad", n, K, derr)
