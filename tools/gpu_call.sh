@@ -20,6 +20,10 @@ for s in "$@"; do
     ncu_wgrad) for i in 4 1; do
         step "ncu k_wgrad_tc shape $i" bash -c "timeout 120 python tools/wgrad_sweep.py $i > gpurun_out/plain_wg$i.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_wgrad_tc -s 3 -c 1 -f -o gpurun_out/wgrad_tc_shape$i python tools/wgrad_sweep.py $i > gpurun_out/ncu_wg$i.log 2>&1; tail -2 gpurun_out/ncu_wg$i.log"
       done ;;
+    ncu_conv6) for a in "495518 27 32 32" "317485 27 64 64" "154605 27 96 96" "59700 27 128 128" "20727 27 160 160" "7332 27 192 192"; do
+        tag=$(echo $a | tr ' ' '_')
+        step "ncu k_conv_tc $a" bash -c "TC_PROFILE_CHECK=0 timeout 120 python tools/tc_profile.py $a 3 > gpurun_out/plain_$tag.log 2>&1 && TC_PROFILE_CHECK=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc -s 2 -c 1 -f -o gpurun_out/conv_tc_$tag python tools/tc_profile.py $a 3 > gpurun_out/ncu_$tag.log 2>&1; tail -2 gpurun_out/ncu_$tag.log"
+      done ;;
     ncu_conv) for a in "495518 27 32 32" "317485 27 64 64"; do
         tag=$(echo $a | tr ' ' '_')
         step "ncu k_conv_tc $a" bash -c "TC_PROFILE_CHECK=0 timeout 120 python tools/tc_profile.py $a 3 > gpurun_out/plain_$tag.log 2>&1 && TC_PROFILE_CHECK=0 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_conv_tc -s 2 -c 1 -f -o gpurun_out/conv_tc_$tag python tools/tc_profile.py $a 3 > gpurun_out/ncu_$tag.log 2>&1; tail -3 gpurun_out/ncu_$tag.log"
