@@ -491,6 +491,23 @@ def run_ours(args, rank, world, local_rank):
         step_e2e(i)
     staged.clear(); loss_pending.clear(); losses.clear()
     torch.cuda.synchronize()
+    # Allocator settling (setup, untimed): rulebook tensors are allocated on the rulebook stream and consumed on the main
+    # stream, so the caching allocator may reuse their blocks only after the consuming kernels have finished; with the host
+    # a step ahead it cudaMalloc()s new blocks instead -- a device synchronisation, up to several 100 ms for the 248 MB stem
+    # table -- until its cache holds enough of them.  Steps are run until a whole cycle of the pool passes without a
+    # device allocation (or 80 steps), so that the timed loops measure the steady state.
+    settle_steps = 0
+    if hasattr(torch.cuda, "memory_stats"):
+        for loop in (step_e2e, step_resident):            # the resident loop last: it is the one timed first
+            quiet, n = 0, 0
+            while n < 60 and quiet < 3 * len(dpool):
+                before = int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
+                loop(n)
+                n += 1
+                quiet = quiet + 1 if int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0)) == before else 0
+            settle_steps += n
+            torch.cuda.synchronize()
+        staged.clear(); loss_pending.clear(); losses.clear()
     # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up steps: its start-up (process launch, NVML
     # initialisation) takes driver locks for a few hundred ms and was measured to cost the first timed loop up to 15%
     # when it fell inside it (2825 vs 3272 events/s in one process); it keeps sampling through the timed region
@@ -500,9 +517,18 @@ def run_ours(args, rank, world, local_rank):
         time.sleep(0.5)
     for i in range(args.warmup):
         step_resident(i)
+    def device_allocs():
+        st = torch.cuda.memory_stats(dev)
+        return int(st.get("num_device_alloc", 0)), int(st.get("num_device_free", 0)), int(st.get("num_alloc_retries", 0))
+    a0 = device_allocs()
     ms, launches = timed(step_resident, args.steps)
+    a1 = device_allocs()
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps)
+    a2 = device_allocs()
+    # cudaMalloc / cudaFree calls of the caching allocator inside the two timed loops (each one is a device synchronisation:
+    # a source of isolated slow steps): [resident loop, e2e loop] x [mallocs, frees, retries]
+    alloc_events = [[a1[i] - a0[i] for i in range(3)], [a2[i] - a1[i] for i in range(3)]]
     while loss_pending:                                   # the last step's loss (its copy finished inside the timed region)
         pev, pslot = loss_pending.pop()
         pev.synchronize()
@@ -635,6 +661,8 @@ def run_ours(args, rank, world, local_rank):
                     "losses_finite": bool(np.all(np.isfinite(losses)))},
             "gpu_launches": launches,
             "host_enqueue_ms_per_step": round(host_enqueue_ms, 3),
+            "device_mallocs_frees_retries_in_timed_loops": alloc_events,
+            "allocator_settle_steps": settle_steps,
             "step_ms_median_max": [[round(float(np.median(t)), 2), round(float(np.max(t)), 2)] for t in step_times],
             "step_ms_resident": step_times[0] if step_times else None,
             "rulebook_ms": round(sum(v["ms_per_step"] for k, v in (breakdown or {}).items() if k.startswith("rulebook")), 3),
