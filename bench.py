@@ -336,6 +336,20 @@ def conv_algorithmic(rec, elem_bytes):
     return flops, by
 
 
+def settle_allocator(step, alloc_count, any_rank, quiet_needed, cap=60):
+    """Run `step(i)` until `quiet_needed` consecutive steps pass without a device allocation on ANY rank (or `cap` steps).
+    `any_rank(flag)` is the collective OR of the ranks' flags: every step contains the gradient all-reduce, so all ranks
+    must leave this loop after the same number of steps -- a rank-local decision deadlocks the job (N > 1).  Returns the
+    number of steps run."""
+    quiet, n = 0, 0
+    while n < cap and quiet < quiet_needed:
+        before = alloc_count()
+        step(n)
+        n += 1
+        quiet = 0 if any_rank(alloc_count() != before) else quiet + 1
+    return n
+
+
 def kernel_source_hash():
     """sha256 of the dominant kernel's sources: ties a committed ncu summary to the build it was captured on."""
     import hashlib
@@ -495,19 +509,22 @@ def run_ours(args, rank, world, local_rank):
     # stream, so the caching allocator may reuse their blocks only after the consuming kernels have finished; with the host
     # a step ahead it cudaMalloc()s new blocks instead -- a device synchronisation, up to several 100 ms for the 248 MB stem
     # table -- until its cache holds enough of them.  Steps are run until a whole cycle of the pool passes without a
-    # device allocation (or 80 steps), so that the timed loops measure the steady state.
+    # device allocation on any rank (or 60 steps), so that the timed loops measure the steady state.
+    def device_alloc_count():
+        return int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
+
+    def any_rank(flag):                                   # the ranks must agree on the number of steps: each one all-reduces
+        if world == 1:
+            return flag
+        t = torch.tensor([1.0 if flag else 0.0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return bool(t.item() > 0)
+
     settle_steps = 0
-    if hasattr(torch.cuda, "memory_stats"):
-        for loop in (step_e2e, step_resident):            # the resident loop last: it is the one timed first
-            quiet, n = 0, 0
-            while n < 60 and quiet < 3 * len(dpool):
-                before = int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0))
-                loop(n)
-                n += 1
-                quiet = quiet + 1 if int(torch.cuda.memory_stats(dev).get("num_device_alloc", 0)) == before else 0
-            settle_steps += n
-            torch.cuda.synchronize()
-        staged.clear(); loss_pending.clear(); losses.clear()
+    for loop in (step_e2e, step_resident):                # the resident loop last: it is the one timed first
+        settle_steps += settle_allocator(loop, device_alloc_count, any_rank, quiet_needed=3 * len(dpool))
+        torch.cuda.synchronize()
+    staged.clear(); loss_pending.clear(); losses.clear()
     # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up steps: its start-up (process launch, NVML
     # initialisation) takes driver locks for a few hundred ms and was measured to cost the first timed loop up to 15%
     # when it fell inside it (2825 vs 3272 events/s in one process); it keeps sampling through the timed region
