@@ -336,17 +336,20 @@ def conv_algorithmic(rec, elem_bytes):
     return flops, by
 
 
-def settle_allocator(step, alloc_count, any_rank, quiet_needed, cap=60):
-    """Run `step(i)` until `quiet_needed` consecutive steps pass without a device allocation on ANY rank (or `cap` steps).
-    `any_rank(flag)` is the collective OR of the ranks' flags: every step contains the gradient all-reduce, so all ranks
-    must leave this loop after the same number of steps -- a rank-local decision deadlocks the job (N > 1).  Returns the
-    number of steps run."""
-    quiet, n = 0, 0
-    while n < cap and quiet < quiet_needed:
+def settle_allocator(step, alloc_count, any_rank, chunk, cap=60):
+    """Run `step(i)` in chunks of `chunk` steps until a whole chunk passes without a device allocation on ANY rank (or
+    `cap` steps).  `any_rank(flag)` is the collective OR of the ranks' flags: every step contains the gradient all-reduce,
+    so all ranks must leave this loop after the same number of steps -- a rank-local decision deadlocks the job (N > 1).
+    The ranks agree once per chunk, not per step, so that inside a chunk the host runs ahead of the GPU exactly as in the
+    timed loops (that is what makes the allocator grow its cache).  Returns the number of steps run."""
+    n = 0
+    while n < cap:
         before = alloc_count()
-        step(n)
-        n += 1
-        quiet = 0 if any_rank(alloc_count() != before) else quiet + 1
+        for _ in range(chunk):
+            step(n)
+            n += 1
+        if not any_rank(alloc_count() != before):
+            break
     return n
 
 
@@ -522,7 +525,7 @@ def run_ours(args, rank, world, local_rank):
 
     settle_steps = 0
     for loop in (step_e2e, step_resident):                # the resident loop last: it is the one timed first
-        settle_steps += settle_allocator(loop, device_alloc_count, any_rank, quiet_needed=3 * len(dpool))
+        settle_steps += settle_allocator(loop, device_alloc_count, any_rank, chunk=3 * len(dpool))
         torch.cuda.synchronize()
     staged.clear(); loss_pending.clear(); losses.clear()
     # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up steps: its start-up (process launch, NVML

@@ -27,12 +27,12 @@ def test_settle_single_rank_counts():
         if i in noisy:
             allocs["n"] += 1
 
-    n = bench.settle_allocator(step, lambda: allocs["n"], lambda f: f, quiet_needed=3)
-    assert n == 8                        # steps 5, 6, 7 are the first three quiet ones in a row
+    n = bench.settle_allocator(step, lambda: allocs["n"], lambda f: f, chunk=3)
+    assert n == 9                        # chunks [0-2], [3-5] allocate, [6-8] is the first quiet one
     allocs["n"] = 0
     n = bench.settle_allocator(lambda i: allocs.__setitem__("n", allocs["n"] + 1), lambda: allocs["n"], lambda f: f,
-                               quiet_needed=3, cap=11)
-    assert n == 11                       # never quiet: the cap ends it
+                               chunk=3, cap=11)
+    assert n == 12                       # never quiet: the cap ends it (after the chunk that crosses it)
 
 
 def _worker(rank, world, port, q):
@@ -41,7 +41,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     allocs = {"n": 0}
-    noisy = {0: {0, 1}, 1: {0, 2, 4}}[rank]          # rank 1's allocator settles later (alone, rank 0 would stop after 5)
+    noisy = {0: {0, 1}, 1: {0, 2, 4}}[rank]          # rank 1's allocator settles later (alone, rank 0 would stop after 6)
     seen = []
 
     def step(i):
@@ -56,7 +56,7 @@ def _worker(rank, world, port, q):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return bool(t.item() > 0)
 
-    n = bench.settle_allocator(step, lambda: allocs["n"], any_rank, quiet_needed=3)
+    n = bench.settle_allocator(step, lambda: allocs["n"], any_rank, chunk=3)
     q.put((rank, n, seen))
     dist.barrier()
     dist.destroy_process_group()
@@ -76,5 +76,5 @@ def test_settle_ranks_agree_world2():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert res[0][0] == res[1][0] == 8                 # the last allocation anywhere is rank 1's step 4 -> steps 5, 6, 7
-    assert res[0][1] == res[1][1] == [2.0 * i + 1.0 for i in range(8)]
+    assert res[0][0] == res[1][0] == 9                 # the last allocation anywhere is rank 1's step 4 -> chunk [6-8] is quiet
+    assert res[0][1] == res[1][1] == [2.0 * i + 1.0 for i in range(9)]
