@@ -720,7 +720,10 @@ def main():
         return
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # 5-minute collective timeout (default 10): a mismatched collective ends the run with an error instead of eating
+        # the caller's time budget; the longest legitimate gap between two collectives is the pool generation (tens of s)
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     try:
         run_ours(args, rank, world, local_rank)
     finally:
