@@ -500,6 +500,11 @@ def run_ours(args, rank, world, local_rank):
             ms = float(t.item())
         return ms, int(launches)
 
+    def note(msg):                                        # progress marks on stderr (stdout carries the one JSON line)
+        if world > 1:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
+    note("pool ready, first steps (graph capture of the heads happens here)")
     # setup, not warm-up: every batch of the pool goes through both loops once so that the caching allocator has seen
     # all tensor sizes (a first-time cudaMalloc is a device synchronisation) before the W warm-up steps start
     for i in range(2 * len(dpool)):
@@ -528,6 +533,7 @@ def run_ours(args, rank, world, local_rank):
         settle_steps += settle_allocator(loop, device_alloc_count, any_rank, chunk=3 * len(dpool))
         torch.cuda.synchronize()
     staged.clear(); loss_pending.clear(); losses.clear()
+    note(f"allocator settled after {settle_steps} steps")
     # the clock sampler (nvidia-smi -lms 100) is started BEFORE the warm-up steps: its start-up (process launch, NVML
     # initialisation) takes driver locks for a few hundred ms and was measured to cost the first timed loop up to 15%
     # when it fell inside it (2825 vs 3272 events/s in one process); it keeps sampling through the timed region
@@ -544,8 +550,10 @@ def run_ours(args, rank, world, local_rank):
     ms, launches = timed(step_resident, args.steps)
     a1 = device_allocs()
     clocks = sampler.stop() if rank == 0 else None
+    note(f"resident loop timed: {ms / args.steps:.2f} ms/step")
     ms_e2e, _ = timed(step_e2e, args.steps)
     a2 = device_allocs()
+    note(f"e2e loop timed: {ms_e2e / args.steps:.2f} ms/step")
     # cudaMalloc / cudaFree calls of the caching allocator inside the two timed loops (each one is a device synchronisation:
     # a source of isolated slow steps): [resident loop, e2e loop] x [mallocs, frees, retries]
     alloc_events = [[a1[i] - a0[i] for i in range(3)], [a2[i] - a1[i] for i in range(3)]]
